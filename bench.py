@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — driver contract: `python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]`.
+
+Prints ONE JSON line (rank 0).  A "step" = one pass of the hot path over one batch of synthetic images per GPU.
+
+Workloads (BASELINE.json configs):
+  depth_beit512     dpt_beit_large_512 @512x512, batch 32/GPU, depth only            (configs[1], the default once built)
+  dav2_stereo       depth_anything_v2 vitl @518 + SBS stereo (polylines) + normal map (configs[2])
+  stereo2048        normalise -> stereo SBS (div 2.5, polylines_sharp) -> normal map on 2048x2048, batch 16/GPU
+                    (north_star's "2048x2048 stereo warp" HBM-roofline target)
+
+`value` = images/s with inputs resident in HBM; `e2e` = same through the public batched API from pinned HOST buffers,
+H2D and D2H inside the timed region; `roofline` = dominant kernel vs MEASURED_PEAKS.json; `cpu_baseline` = the oracle
+(C restatement of the reference's CPU path) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = mx
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic data
+# ---------------------------------------------------------------------------------------------------------------------
+def make_images(B, H, W, rank):
+    from synth import synth_depth_u16, synth_rgb
+    nuniq = min(B, 4)
+    rgbs = [synth_rgb(H, W, 100 * rank + i) for i in range(nuniq)]
+    preds = [(synth_depth_u16(H, W, 100 * rank + i).astype(np.float32) / 1000.0 - 7.0) for i in range(nuniq)]
+    rgb = np.stack([rgbs[i % nuniq] for i in range(B)])
+    pred = np.stack([preds[i % nuniq] for i in range(B)])
+    return rgb, pred
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workload: stereo2048  (normalise -> stereo SBS -> normal map), all HBM-side kernels
+# ---------------------------------------------------------------------------------------------------------------------
+class Stereo2048:
+    name = "stereo2048"
+    H = W = 2048
+    B = 16
+    dtype = "f64"  # the stereo / normal-map arithmetic type (fp64, truncating to u8); normalise is f32
+    fill = "polylines_sharp"
+    launches_per_step = 3 + 3 + 1  # normalise (init, minmax, quantise) + stereo (init, minmax, row) + normal map
+
+    def __init__(self, dev, rank):
+        import torch
+        self.dev = dev
+        rgb, pred = make_images(self.B, self.H, self.W, rank)
+        self.rgb_h = torch.from_numpy(rgb).pin_memory()
+        self.pred_h = torch.from_numpy(pred).pin_memory()
+        self.rgb = self.rgb_h.to(dev)
+        self.pred = self.pred_h.to(dev)
+        self.kernel_ms = []
+
+    def config(self):
+        return {"workload": "synthetic 2048x2048 RGB + float32 prediction -> u16 depth -> SBS stereo (divergence 2.5, "
+                            "polylines_sharp) -> normal map (Sobel 3)", "batch_per_gpu": self.B, "height": self.H,
+                "width": self.W, "l2_policy": "inputs+outputs per step (1.0 GB) exceed the 126 MB L2"}
+
+    def step(self, rgb, pred, time_kernel=False):
+        import torch
+        from depthmap_b200.core import normalize_prediction_batch
+        from depthmap_b200.normalmap_generation import create_normalmap_batch
+        from depthmap_b200.stereoimage_generation import create_stereoimages_batch
+        depth = normalize_prediction_batch(pred, False)
+        if time_kernel:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        sbs = create_stereoimages_batch(rgb, depth, 2.5, 0.0, ['left-right'], 0.0, 1.0, self.fill)[0]
+        if time_kernel:
+            e1.record()
+            self._ev = (e0, e1)
+        normal = create_normalmap_batch(depth)
+        return depth, sbs, normal
+
+    def step_resident(self, time_kernel=False):
+        return self.step(self.rgb, self.pred, time_kernel)
+
+    def step_e2e(self):
+        rgb = self.rgb_h.to(self.dev, non_blocking=True)
+        pred = self.pred_h.to(self.dev, non_blocking=True)
+        outs = self.step(rgb, pred)
+        return [o.to("cpu", non_blocking=True) for o in outs]
+
+    def e2e_bytes(self):
+        h2d = self.rgb_h.numel() + self.pred_h.numel() * 4
+        d2h = self.B * self.H * self.W * (2 + 6 + 3)
+        return h2d, d2h
+
+    def roofline(self, peaks, kernel_ms):
+        alg = 11.0 * self.H * self.W * self.B  # 3 (RGB) + 2 (depth) in, 6 (two eyes) out per pixel
+        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "stereo_row_kernel (+ u16 min/max pre-pass)", "achieved": achieved,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peaks["source"], "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
+                "note": "exact-fp64 polylines is FP64/latency bound, not HBM bound; see DESIGN.md"}
+
+    def cpu_sample(self, nthreads):
+        """oracle on one 2048^2 image (normalise + stereo + normal map)."""
+        from oracle import normalmap as onm
+        from oracle import stereo as ost
+        rgb = self.rgb_h[0].numpy()
+        pred = self.pred_h[0].numpy()
+        t0 = time.perf_counter()
+        d = onm.normalize_to_u16(pred, False)
+        ost.create_stereoimages(rgb, d, 2.5, 0.0, ['left-right'], 0.0, 1.0, self.fill, return_arrays=True, nthreads=nthreads)
+        onm.create_normalmap(d, return_array=True)
+        return 1, time.perf_counter() - t0
+
+
+WORKLOADS = {"stereo2048": Stereo2048}
+try:
+    from bench_models import MODEL_WORKLOADS  # depth-network workloads, added once the tensor-core path is built
+    WORKLOADS.update(MODEL_WORKLOADS)
+except ImportError:
+    pass
+DEFAULT_WORKLOAD = "depth_beit512" if "depth_beit512" in WORKLOADS else ("dav2_stereo" if "dav2_stereo" in WORKLOADS else "stereo2048")
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on this box's host cores."""
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    wl_cls = WORKLOADS[args.workload]
+    wl = wl_cls.__new__(wl_cls)
+    cores = os.cpu_count() or 1
+    if hasattr(wl_cls, "reference_arm"):
+        line = wl_cls.reference_arm(args, cores)
+    else:
+        import torch
+        rgb, pred = make_images(1, wl_cls.H, wl_cls.W, 0)
+        wl.rgb_h, wl.pred_h = torch.from_numpy(rgb), torch.from_numpy(pred)
+        for _ in range(args.warmup):
+            wl.cpu_sample(cores)
+        t = []
+        for _ in range(args.steps):
+            n, dt = wl.cpu_sample(cores)
+            t.append(dt / n)
+        ms = float(np.mean(t)) * 1e3
+        val = 1000.0 / ms
+        line = {"metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": wl_cls.dtype, "data": "synthetic", "impl": "reference",
+                "config": {"workload": wl_cls.config(wl)["workload"], "sample": "1 image per step"},
+                "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                                 "sample": "1 image per step through oracle/ (C restatement, OpenMP over rows)"},
+                "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    peaks = _peaks()
+    wl = WORKLOADS[args.workload](dev, rank)
+
+    gather_bufs = None
+
+    def full_step(time_kernel=False):
+        outs = wl.step_resident(time_kernel)
+        if world > 1:  # the path's one exchange: all-gather of the finished tensors over NVLink
+            nonlocal gather_bufs
+            flat = [o.reshape(-1).view(torch.uint8) if o.dtype != torch.uint8 else o.reshape(-1) for o in outs]
+            if gather_bufs is None:
+                gather_bufs = [torch.empty(world * f.numel(), dtype=torch.uint8, device=dev) for f in flat]
+            for f, g in zip(flat, gather_bufs):
+                dist.all_gather_into_tensor(g, f)
+        return outs
+
+    for _ in range(args.warmup):
+        full_step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs ------------------------------------------------------------------
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_events = []
+    e0.record()
+    for _ in range(args.steps):
+        full_step(time_kernel=True)
+        if hasattr(wl, "_ev"):
+            kernel_events.append(wl._ev)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events])) if kernel_events else None
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region ----------------------------------------------------
+    for _ in range(2):
+        wl.step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        wl.step_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item()) / args.steps
+    h2d, d2h = wl.e2e_bytes()
+
+    if rank == 0:
+        value = wl.B * world / (ms_step * 1e-3)
+        line = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
+                "clocks": clocks, "gpu_launches": wl.launches_per_step * args.steps,
+                "e2e": {"value": wl.B * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e}}
+        if kernel_ms is not None:
+            line["roofline"] = wl.roofline(peaks, kernel_ms)
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            cores = os.cpu_count() or 1
+            wl.cpu_sample(cores)
+            n, dt = wl.cpu_sample(cores)
+            line["cpu_baseline"] = {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} image(s) of the same workload through oracle/ (C restatement of the reference CPU path, OpenMP over rows), {dt:.2f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,99 @@
+/*
+ * depthmap_b200 — C-ABI of the B200-native depth -> 16-bit depth -> stereo / normal-map hot path.
+ *
+ * Every entry point replaces one Python-level operator of thygate/stable-diffusion-webui-depthmap-script
+ * (reference @ e4df29bc); the reference has no FFI of its own, so the binding a maintainer adds is the ctypes stub
+ * shown in INTEGRATION.md.  Conventions:
+ *   - plain C types only; every pointer is DEVICE memory owned by the caller unless it is named *_host;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host synchronisation
+ *     and allocates nothing: scratch comes from the caller through (workspace, workspace_bytes), sized by the
+ *     matching *_workspace_bytes() query;
+ *   - return value: DM_OK (0) or a negative dm_status; dm_last_error() gives the message for the calling thread;
+ *   - images are batched, B images of identical H x W, densely packed: rgb = [B][H][W][3] u8, depth = [B][H][W].
+ */
+#ifndef DEPTHMAP_B200_H
+#define DEPTHMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dm_status {
+    DM_OK = 0,
+    DM_E_INVALID = -1,      /* bad argument (Python face raises ValueError / the reference's own exception) */
+    DM_E_CUDA = -2,         /* CUDA runtime error other than OOM */
+    DM_E_OOM = -3,          /* message contains "out of memory" so src/core.py:310 still recognises it */
+    DM_E_UNSUPPORTED = -4,  /* valid request outside the implemented envelope (e.g. row too wide for smem) */
+    DM_E_WORKSPACE = -5     /* workspace too small */
+} dm_status;
+
+const char *dm_last_error(void);
+int dm_version(void);
+/* Name of the device the library would run on, "" if no CUDA device; never throws. */
+int dm_device_name(char *buf_host, int buf_len);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * N1 — funnel post-processing of a model prediction: per-image min/max, invert, optional "Range" clip, normalise,
+ * convert_to_i16.            replaces  src/core.py:189-211 (model branch) + src/core.py:44-50
+ * clip_mode: 0 none, 1 "Range" (clip_far / clip_near as in GenerationOptions CLIPDEPTH_FAR / CLIPDEPTH_NEAR).
+ * All arithmetic float32, as numpy does it.  Degenerate image (max-min <= DBL_EPSILON) -> all-zero output.
+ * degenerate_flags (optional, may be NULL): int32[B], 1 where the image was degenerate.
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t dm_normalize_u16_workspace_bytes(int B);
+int dm_normalize_u16(const float *pred, int B, int H, int W, int invert, int clip_mode, float clip_far,
+                     float clip_near, uint16_t *depth_out, int32_t *degenerate_flags, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * S1-S5 — stereo pair: per-row depth-driven warp + gap fill + packing.
+ *            replaces  src/stereoimage_generation.py:13-74 (create_stereoimages),
+ *                      :77-92 (apply_stereo_divergence), :95-159 (naive family), :162-283 (polylines), :286-307
+ * depth_kind: DM_DEPTH_U16 -> `depth` is uint16; (d-min)/(max-min) is evaluated in fp64 per image on the device;
+ *             DM_DEPTH_ND64 -> `depth` is float64 already-normalised depth (host face handles exotic dtypes).
+ * Per eye e in {0 = left, 1 = right}: div_px[e], sep_px[e] (pixels, as the reference computes them in Python) and
+ * eye_mode[e]: DM_EYE_WARP (run the algorithm), DM_EYE_IDENTITY (reference skips the warp: eye = source image),
+ * DM_EYE_SKIP (eye not needed for the requested packing).
+ * pack: DM_PACK_STRIDED  eye e is written to out[e] with dst_row_stride[e] / dst_img_stride[e] (bytes); covers
+ *                        left-right, right-left, top-bottom, bottom-top, left-only, only-right by pointer arithmetic;
+ *       DM_PACK_ANAGLYPH out[0] receives R from eye a0, G,B from eye 1-a0 where a0 = anaglyph_red_eye (0: red-cyan,
+ *                        1: cyan-red-reverse); uses dst strides [0].
+ * ------------------------------------------------------------------------------------------------------------- */
+enum { DM_DEPTH_U16 = 0, DM_DEPTH_ND64 = 1 };
+enum { DM_FILL_NONE = 0, DM_FILL_NAIVE = 1, DM_FILL_NAIVE_INTERPOLATING = 2, DM_FILL_POLYLINES_SOFT = 3,
+       DM_FILL_POLYLINES_SHARP = 4 };
+enum { DM_EYE_WARP = 0, DM_EYE_IDENTITY = 1, DM_EYE_SKIP = 2 };
+enum { DM_PACK_STRIDED = 0, DM_PACK_ANAGLYPH = 1 };
+
+typedef struct dm_stereo_params {
+    double div_px[2];
+    double sep_px[2];
+    double exponent;          /* stereo_offset_exponent */
+    int32_t eye_mode[2];
+    int32_t fill;             /* DM_FILL_* */
+    int32_t pack;             /* DM_PACK_* */
+    int32_t anaglyph_red_eye; /* 0 or 1 */
+    int32_t depth_kind;       /* DM_DEPTH_* */
+    int32_t reserved;
+    int64_t dst_row_stride[2];
+    int64_t dst_img_stride[2];
+} dm_stereo_params;
+
+size_t dm_stereo_workspace_bytes(int B, int H, int W);
+int dm_stereo(const uint8_t *rgb, const void *depth, int B, int H, int W, const dm_stereo_params *params_host,
+              uint8_t *out0, uint8_t *out1, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * M1 — tangent-space normal map.           replaces  src/normalmap_generation.py:5-56 (create_normalmap)
+ * pre_blur / sobel / post_blur: kernel sizes, <= 0 means None (sobel <= 0 selects the np.gradient branch).
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t dm_normalmap_workspace_bytes(int B, int H, int W, int pre_blur, int sobel, int post_blur);
+int dm_normalmap(const uint16_t *depth, int B, int H, int W, int pre_blur, int sobel, int post_blur, int invert,
+                 uint8_t *rgb_out, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEPTHMAP_B200_H */

@@ -10,8 +10,8 @@
  * published algorithm: getSobelKernels (repeated [1 1] smoothing then [-1 1] differencing, unnormalised),
  * getGaussianKernel (exp(-x^2/(2 sigma^2)) normalised to sum 1, computed in double), separable row-then-column
  * filtering.  For u16 input without pre-blur every Sobel partial sum is an exact multiple of 2^-8 below 2^53, so the
- * summation order cannot matter; with a Gaussian pre-blur the tap order follows OpenCV's symmetric filters
- * (centre tap first, then pairs (x[-k] + x[+k]) * w[k] outward).
+ * summation order cannot matter for small kernels; large Sobel kernels (binomial taps up to C(30,15)) and Gaussian
+ * blurs round, so the tap order follows OpenCV's CV_64F filter engine (see sep_filter).
  */
 #include <math.h>
 #include <stdint.h>
@@ -65,38 +65,36 @@ static void gaussian_kernel(int n, double sigma, double *k) {
     for (int i = 0; i < n; ++i) k[i] *= sum;
 }
 
-/* separable correlation, channels interleaved (cn), REFLECT_101.  symmetric != 0 selects the centre-then-pairs order. */
+/* separable correlation, channels interleaved (cn), REFLECT_101, following OpenCV's CV_64F filter engine:
+ *   row pass    = RowFilter<double,double>: plain left-to-right accumulation, first tap initialises the sum;
+ *   column pass = SymmColumnFilter: symmetric kernels   s = k[c]*x[c];  s += k[c+j]*(x[c+j] + x[c-j]), j = 1..r
+ *                                   asymmetric kernels  s = 0;          s += k[c+j]*(x[c+j] - x[c-j]), j = 1..r
+ * ysym: +1 symmetric column kernel, -1 anti-symmetric column kernel. */
 static void sep_filter(const double *src, double *dst, int h, int w, int cn, const double *kx, int nx,
-                       const double *ky, int ny, int symmetric) {
+                       const double *ky, int ny, int ysym) {
     double *tmp = (double *)malloc(sizeof(double) * (size_t)h * w * cn);
     int rx = nx / 2, ry = ny / 2;
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x)
             for (int c = 0; c < cn; ++c) {
-                double s;
-                if (symmetric) {
-                    s = kx[rx] * src[((size_t)y * w + x) * cn + c];
-                    for (int k = 1; k <= rx; ++k)
-                        s += kx[rx + k] * (src[((size_t)y * w + reflect101(x - k, w)) * cn + c] +
-                                           src[((size_t)y * w + reflect101(x + k, w)) * cn + c]);
-                } else {
-                    s = 0.0;
-                    for (int k = 0; k < nx; ++k) s += kx[k] * src[((size_t)y * w + reflect101(x + k - rx, w)) * cn + c];
-                }
+                double s = kx[0] * src[((size_t)y * w + reflect101(x - rx, w)) * cn + c];
+                for (int k = 1; k < nx; ++k) s += kx[k] * src[((size_t)y * w + reflect101(x + k - rx, w)) * cn + c];
                 tmp[((size_t)y * w + x) * cn + c] = s;
             }
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x)
             for (int c = 0; c < cn; ++c) {
                 double s;
-                if (symmetric) {
+                if (ysym > 0) {
                     s = ky[ry] * tmp[((size_t)y * w + x) * cn + c];
                     for (int k = 1; k <= ry; ++k)
-                        s += ky[ry + k] * (tmp[((size_t)reflect101(y - k, h) * w + x) * cn + c] +
-                                           tmp[((size_t)reflect101(y + k, h) * w + x) * cn + c]);
+                        s += ky[ry + k] * (tmp[((size_t)reflect101(y + k, h) * w + x) * cn + c] +
+                                           tmp[((size_t)reflect101(y - k, h) * w + x) * cn + c]);
                 } else {
                     s = 0.0;
-                    for (int k = 0; k < ny; ++k) s += ky[k] * tmp[((size_t)reflect101(y + k - ry, h) * w + x) * cn + c];
+                    for (int k = 1; k <= ry; ++k)
+                        s += ky[ry + k] * (tmp[((size_t)reflect101(y + k, h) * w + x) * cn + c] -
+                                           tmp[((size_t)reflect101(y - k, h) * w + x) * cn + c]);
                 }
                 dst[((size_t)y * w + x) * cn + c] = s;
             }
@@ -121,12 +119,12 @@ int oracle_normalmap(const uint16_t *depth, int h, int w, int pre_blur, int sobe
     }
     if (pre_blur > 0) {                                   /* :23-24 GaussianBlur(z, (k,k), sigma=k) */
         gaussian_kernel(pre_blur, (double)pre_blur, kbuf);
-        sep_filter(z, z, h, w, 1, kbuf, pre_blur, kbuf, pre_blur, 1);
+        sep_filter(z, z, h, w, 1, kbuf, pre_blur, kbuf, pre_blur, +1);
     }
     if (sobel > 0) {                                      /* :27-29 */
         int nd_ = sobel_kernel(sobel, 1, kbuf), ns = sobel_kernel(sobel, 0, kbuf2);
-        sep_filter(z, zx, h, w, 1, kbuf, nd_, kbuf2, ns, 0);
-        sep_filter(z, zy, h, w, 1, kbuf2, ns, kbuf, nd_, 0);
+        sep_filter(z, zx, h, w, 1, kbuf, nd_, kbuf2, ns, +1);
+        sep_filter(z, zy, h, w, 1, kbuf2, ns, kbuf, nd_, -1);
     } else {                                              /* :31 np.gradient, edge_order 1 */
         for (int y = 0; y < h; ++y)
             for (int x = 0; x < w; ++x) {
@@ -148,7 +146,7 @@ int oracle_normalmap(const uint16_t *depth, int h, int w, int pre_blur, int sobe
     }
     if (post_blur > 0) {                                  /* :42-48 */
         gaussian_kernel(post_blur, (double)post_blur, kbuf);
-        sep_filter(nrm, nrm, h, w, 3, kbuf, post_blur, kbuf, post_blur, 1);
+        sep_filter(nrm, nrm, h, w, 3, kbuf, post_blur, kbuf, post_blur, +1);
         for (size_t i = 0; i < n; ++i) {
             double a = nrm[i * 3], b = nrm[i * 3 + 1], c = nrm[i * 3 + 2];
             double nn = sqrt(a * a + b * b + c * c);

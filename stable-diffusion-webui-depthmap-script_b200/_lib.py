@@ -1,0 +1,105 @@
+"""ctypes binding of include/depthmap_b200.h.  Fails loudly: no library -> ImportError-like RuntimeError, no GPU -> RuntimeError."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_native", "libdepthmap_b200.so")
+
+DM_OK, DM_E_INVALID, DM_E_CUDA, DM_E_OOM, DM_E_UNSUPPORTED, DM_E_WORKSPACE = 0, -1, -2, -3, -4, -5
+DM_DEPTH_U16, DM_DEPTH_ND64 = 0, 1
+DM_FILL = {"none": 0, "naive": 1, "naive_interpolating": 2, "polylines_soft": 3, "polylines_sharp": 4}
+DM_EYE_WARP, DM_EYE_IDENTITY, DM_EYE_SKIP = 0, 1, 2
+DM_PACK_STRIDED, DM_PACK_ANAGLYPH = 0, 1
+
+
+class StereoParams(ctypes.Structure):
+    _fields_ = [
+        ("div_px", ctypes.c_double * 2),
+        ("sep_px", ctypes.c_double * 2),
+        ("exponent", ctypes.c_double),
+        ("eye_mode", ctypes.c_int32 * 2),
+        ("fill", ctypes.c_int32),
+        ("pack", ctypes.c_int32),
+        ("anaglyph_red_eye", ctypes.c_int32),
+        ("depth_kind", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("dst_row_stride", ctypes.c_int64 * 2),
+        ("dst_img_stride", ctypes.c_int64 * 2),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+
+# every symbol include/depthmap_b200.h declares; tests check the built library exports all of them
+EXPORTS = [
+    "dm_last_error", "dm_version", "dm_device_name",
+    "dm_normalize_u16_workspace_bytes", "dm_normalize_u16",
+    "dm_stereo_workspace_bytes", "dm_stereo",
+    "dm_normalmap_workspace_bytes", "dm_normalmap",
+]
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"depthmap_b200: native library missing ({LIB_PATH}). Build it with "
+                f"`python {os.path.join(_HERE, 'csrc', 'build.py')}` — there is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        c = ctypes
+        vp, i32, i64, f32, sz = c.c_void_p, c.c_int, c.c_int64, c.c_float, c.c_size_t
+        L.dm_last_error.restype = c.c_char_p
+        L.dm_version.restype = i32
+        L.dm_device_name.argtypes = [c.c_char_p, i32]
+        L.dm_normalize_u16_workspace_bytes.argtypes = [i32]
+        L.dm_normalize_u16_workspace_bytes.restype = sz
+        L.dm_normalize_u16.argtypes = [vp, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp, sz, vp]
+        L.dm_stereo_workspace_bytes.argtypes = [i32, i32, i32]
+        L.dm_stereo_workspace_bytes.restype = sz
+        L.dm_stereo.argtypes = [vp, vp, i32, i32, i32, c.POINTER(StereoParams), vp, vp, vp, sz, vp]
+        L.dm_normalmap_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+        L.dm_normalmap_workspace_bytes.restype = sz
+        L.dm_normalmap.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+        _bind_optional(L)
+        _lib = L
+        return L
+
+
+def _bind_optional(L):
+    """Model entry points (present once the tensor-core units are linked in)."""
+    c = ctypes
+    vp, i32, i64, f32, sz = c.c_void_p, c.c_int, c.c_int64, c.c_float, c.c_size_t
+    if hasattr(L, "dm_gemm_bf16"):
+        L.dm_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]
+
+
+def check(rc: int, what: str = ""):
+    if rc == DM_OK:
+        return
+    msg = load().dm_last_error().decode("utf-8", "replace")
+    if rc == DM_E_OOM:
+        raise RuntimeError(f"CUDA out of memory. {msg}")  # src/core.py:310 matches 'out of memory'
+    if rc == DM_E_INVALID:
+        raise ValueError(msg or what)
+    if rc == DM_E_UNSUPPORTED:
+        raise NotImplementedError(msg or what)
+    raise RuntimeError(f"depthmap_b200 {what} failed ({rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("depthmap_b200: no CUDA device visible; the B200 kernels have no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,556 @@
+// S1-S5 — stereo pair generation.  Replaces src/stereoimage_generation.py:13-307 of the reference.
+//
+// One CTA owns one image row (rows are independent in every fill mode, :101/:174) and produces BOTH eyes for it from
+// a single read of the row (3 B/px RGB + 2 B/px depth), writing the packed result once (6 B/px SBS, 3 B/px anaglyph):
+// the compulsory 11 B/px (8 B/px anaglyph) of SURVEY §8d and nothing else touches HBM.
+//
+// The reference's row algorithms are sequential sweeps; they are re-derived here as data-parallel forms that give the
+// same bytes (compiled with -fmad=false: numba emits no FMA contraction; all arithmetic fp64 like the reference):
+//
+//  naive family (:95-159)  forward scatter where "the last writer in sweep order wins" == atomicMax (div_px < 0,
+//      ascending sweep) / atomicMin (otherwise) of the SOURCE column per destination.  `naive` fill = nearest filled
+//      neighbour, right before left, within |int(div_px)|+1.  `naive_interpolating` = closed form of the left-to-right
+//      gap walk: with V = filled & non-black, a pixel p lies in a gap iff an unfilled pixel exists in (lastV(p), p];
+//      the gap is [first such pixel, next V after p) and its borders are read from the pre-fill row (three scans).
+//
+//  polylines (:162-283)  the morphed polyline never self-intersects (proof in the reference, :200-212), so at any x
+//      the segment with maximal closeness is the FIRST (div_px >= 0) or LAST (div_px < 0) segment, in original vertex
+//      order, that spans x.  Hence winner(x) = (first t with prefixmax(X)[t] >= x) - 1, resp. last t with
+//      suffixmin(X)[t] < x: one scan + one binary search replaces the active-segment list.  The stable insertion sort
+//      becomes a counting sort by floor(x) (one bucket per output pixel) + an in-bucket insertion sort on (x, index).
+//      Each output pixel then walks its own sub-intervals in sorted order, accumulating colour*significance from 0.5
+//      exactly as :229-281 does, and truncates.  Distinct non-adjacent spanning segments differ in closeness by >= 0.1
+//      (sharp) / 1 (soft) px, 12 orders of magnitude above fp64 rounding, so the reformulation is exact except on
+//      exact ties of vertex x (measure-zero; stable order is still honoured for the sub-interval sequence).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace dm {
+
+struct StereoArgs {
+    const uint8_t *rgb;
+    const void *depth;
+    const uint32_t *minmax;  // [B][2] u16 min / max (DM_DEPTH_U16 only)
+    int H, W;
+    double exponent;
+    double div_px[2], sep_px[2];
+    int eye_mode[2];
+    int fill, pack, red_eye, depth_kind;
+    int naive_lim;  // |int(div_px)| per eye is derived on device; kept for clarity
+    uint8_t *out[2];
+    int64_t row_stride[2], img_stride[2];
+};
+
+constexpr double EPSILON = 1e-7;
+
+// ---------------------------------------------------------------------------------------------------------------
+// block-wide inclusive scans over shared memory (chunk per thread + shuffle scan of chunk totals)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, typename Op>
+__device__ void block_scan_inclusive(T *data, int n, T identity, Op op, bool reverse, T *warp_tot /*[32]*/) {
+    const int T_ = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (n + T_ - 1) / T_;
+    const int beg = tid * chunk, end = min(n, beg + chunk);
+    T acc = identity;
+    for (int i = beg; i < end; ++i) {
+        const int j = reverse ? n - 1 - i : i;
+        acc = op(acc, data[j]);
+        data[j] = acc;
+    }
+    // exclusive scan of per-thread totals
+    T incl = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = op(v, incl);
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < (T_ >> 5) ? warp_tot[lane] : identity;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w = op(v, w);
+        }
+        warp_tot[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    T excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = identity;
+    if (warp > 0) excl = op(warp_tot[warp - 1], excl);
+    for (int i = beg; i < end; ++i) {
+        const int j = reverse ? n - 1 - i : i;
+        data[j] = op(excl, data[j]);
+    }
+    __syncthreads();
+}
+
+struct OpMaxD { __device__ double operator()(double a, double b) const { return b > a ? b : a; } };
+struct OpMinD { __device__ double operator()(double a, double b) const { return b < a ? b : a; } };
+struct OpMaxI { __device__ int operator()(int a, int b) const { return max(a, b); } };
+struct OpMinI { __device__ int operator()(int a, int b) const { return min(a, b); } };
+struct OpAddI { __device__ int operator()(int a, int b) const { return a + b; } };
+
+// coalesced store of `nbytes` from shared `src` to global `dst` (arbitrary alignment)
+__device__ __forceinline__ void store_row(uint8_t *dst, const uint8_t *src, int nbytes) {
+    const int tid = threadIdx.x, T_ = blockDim.x;
+    const int head = (int)((16 - ((uintptr_t)dst & 15)) & 15);
+    const int h = head < nbytes ? head : nbytes;
+    for (int i = tid; i < h; i += T_) dst[i] = src[i];
+    const int nvec = (nbytes - h) >> 4;
+    for (int i = tid; i < nvec; i += T_) {
+        const uint8_t *s = src + h + i * 16;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            w[k] = (uint32_t)s[4 * k] | ((uint32_t)s[4 * k + 1] << 8) | ((uint32_t)s[4 * k + 2] << 16) | ((uint32_t)s[4 * k + 3] << 24);
+        *reinterpret_cast<uint4 *>(dst + h + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    const int tail0 = h + nvec * 16;
+    for (int i = tail0 + tid; i < nbytes; i += T_) dst[i] = src[i];
+}
+
+__device__ __forceinline__ double pow_ref(double nd, double e, int kind) {
+    // kind 0: e == 1 (pow(x,1) == x exactly); 1: e == 2 (x*x, correctly rounded); 2: general (CUDA pow, <= 2 ulp)
+    if (kind == 0) return nd;
+    if (kind == 1) return nd * nd;
+    return pow(nd, e);
+}
+
+__device__ __forceinline__ uint8_t f64_to_u8_wrap(double v) {
+    if (!(v > -2.0e9 && v < 2.0e9)) return 0;
+    return (uint8_t)(int)v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the row kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct RowSmem {
+    uint8_t *src;      // [3W]
+    uint8_t *eye[2];   // [3W] each
+    double *ndp;       // [W]   nd ** exponent
+    double *pm;        // [n]   prefix max / suffix min of vertex x (polylines)
+    uint16_t *order;   // [n]   vertex indices sorted by (x, index) (polylines)
+    int *off;          // [W+3] bucket offsets (polylines) / scratch ints (naive: winner[W])
+    int *cur;          // [W+3] bucket cursors (polylines) / scratch ints (naive_interpolating)
+    int *aux;          // [W+1] naive_interpolating third scan
+    double *wtot_d;    // [32]
+    int *wtot_i;       // [32]
+};
+
+template <bool SHARP>
+struct Poly {
+    int W, n;
+    double div_px, sep_px;
+    const double *ndp;
+    __device__ __forceinline__ int srccol(int t) const {
+        if (t == 0) return 0;
+        if (t == n - 1) return W - 1;
+        return SHARP ? ((t - 1) >> 1) : (t - 1);
+    }
+    // :177-192 vertex x in ORIGINAL order
+    __device__ __forceinline__ double X(int t) const {
+        if (t == 0) return -1.0 * (double)W;
+        if (t == n - 1) return 2.0 * (double)W;
+        const int col = SHARP ? ((t - 1) >> 1) : (t - 1);
+        const double coord_d = ndp[col] * div_px;
+        const double coord_x = (double)col + 0.5 + coord_d + sep_px;
+        if (!SHARP) return coord_x;
+        return ((t - 1) & 1) ? coord_x + 0.45 : coord_x - 0.45;
+    }
+};
+
+template <bool SHARP>
+__device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double sep_px, uint8_t *dst) {
+    const int tid = threadIdx.x, T_ = blockDim.x;
+    Poly<SHARP> P;
+    P.W = W; P.n = SHARP ? 2 * W + 2 : W + 2; P.div_px = div_px; P.sep_px = sep_px; P.ndp = sm.ndp;
+    const int n = P.n;
+    const bool fwd = !(div_px < 0.0);
+
+    // 1. vertex x, then prefix-max (fwd) or suffix-min (bwd) in original order
+    for (int t = tid; t < n; t += T_) sm.pm[t] = P.X(t);
+    for (int b = tid; b < W + 3; b += T_) sm.off[b] = 0;
+    __syncthreads();
+    // 2. counting sort by bucket(x): 0 for x<0, 1+floor(x) for 0<=x<W, W+1 for x>=W   (vertices 0..n-2 only, :214)
+    for (int t = tid; t < n - 1; t += T_) {
+        const double x = sm.pm[t];
+        int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
+        atomicAdd(&sm.off[b], 1);
+    }
+    __syncthreads();
+    if (fwd) block_scan_inclusive<double>(sm.pm, n, -INFINITY, OpMaxD(), false, sm.wtot_d);
+    else block_scan_inclusive<double>(sm.pm, n, INFINITY, OpMinD(), true, sm.wtot_d);
+    block_scan_inclusive<int>(sm.off, W + 2, 0, OpAddI(), false, sm.wtot_i);  // inclusive: off[b] = end of bucket b
+    for (int b = tid; b < W + 2; b += T_) sm.cur[b] = b == 0 ? 0 : sm.off[b - 1];
+    __syncthreads();
+    for (int t = tid; t < n - 1; t += T_) {
+        const double x = P.X(t);
+        int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
+        const int pos = atomicAdd(&sm.cur[b], 1);
+        sm.order[pos] = (uint16_t)t;
+    }
+    if (tid == 0) sm.order[n - 1] = (uint16_t)(n - 1);
+    __syncthreads();
+    // 3. order inside buckets by (x, original index)
+    for (int b = tid; b < W + 2; b += T_) {
+        const int beg = b == 0 ? 0 : sm.off[b - 1], end = sm.off[b];
+        if (end - beg < 2) continue;
+        if (b == 0) {  // only its maximum matters (predecessor of pixel 0): move it last
+            int bi = beg; double bx = P.X(sm.order[beg]); int bt = sm.order[beg];
+            for (int i = beg + 1; i < end; ++i) {
+                const int t = sm.order[i]; const double x = P.X(t);
+                if (x > bx || (x == bx && t > bt)) { bx = x; bt = t; bi = i; }
+            }
+            const uint16_t tmp = sm.order[end - 1]; sm.order[end - 1] = sm.order[bi]; sm.order[bi] = tmp;
+        } else if (b == W + 1) {  // only its minimum matters (successor of the last in-range vertex): move it first
+            int bi = beg; double bx = P.X(sm.order[beg]); int bt = sm.order[beg];
+            for (int i = beg + 1; i < end; ++i) {
+                const int t = sm.order[i]; const double x = P.X(t);
+                if (x < bx || (x == bx && t < bt)) { bx = x; bt = t; bi = i; }
+            }
+            const uint16_t tmp = sm.order[beg]; sm.order[beg] = sm.order[bi]; sm.order[bi] = tmp;
+        } else {
+            for (int i = beg + 1; i < end; ++i) {
+                const int t = sm.order[i]; const double x = P.X(t);
+                int j = i - 1;
+                while (j >= beg) {
+                    const int tj = sm.order[j]; const double xj = P.X(tj);
+                    if (xj > x || (xj == x && tj > t)) { sm.order[j + 1] = (uint16_t)tj; --j; } else break;
+                }
+                sm.order[j + 1] = (uint16_t)t;
+            }
+        }
+    }
+    __syncthreads();
+    // 4. rasterise: one output pixel per thread iteration (:228-281)
+    for (int col = tid; col < W; col += T_) {
+        double c0 = 0.5, c1 = 0.5, c2 = 0.5;
+        int i = sm.off[col] - 1;  // last vertex with x < col  (end of bucket `col` == pixels < col)
+        double xi = P.X(sm.order[i]);
+        const double colf = (double)col, colp = (double)(col + 1);
+        while (xi < colp) {
+            const double xn = P.X(sm.order[i + 1]);
+            const double coord_from = (xi > colf ? xi : colf) + EPSILON;
+            const double coord_to = (xn < colp ? xn : colp) - EPSILON;
+            const double significance = coord_to - coord_from;
+            const double coord_center = coord_from + 0.5 * significance;
+            // winning segment s = vertices (s, s+1) in original order
+            int s;
+            if (fwd) {  // first t with pm[t] >= center
+                int lo = 0, hi = n - 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.pm[mid] >= coord_center) hi = mid; else lo = mid + 1; }
+                s = lo - 1;
+            } else {    // last t with pm[t] < center
+                int lo = 0, hi = n - 1;
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sm.pm[mid] < coord_center) lo = mid; else hi = mid - 1; }
+                s = lo;
+            }
+            s = max(0, min(s, n - 2));
+            const int col_l = P.srccol(s), col_r = P.srccol(s + 1);
+            const uint8_t *pl = sm.src + 3 * col_l;
+            if (col_l == col_r) {
+                c0 += (double)pl[0] * significance;
+                c1 += (double)pl[1] * significance;
+                c2 += (double)pl[2] * significance;
+            } else {
+                const uint8_t *pr = sm.src + 3 * col_r;
+                const double x0 = P.X(s), x1 = P.X(s + 1);
+                const double ip_k = (coord_center - x0) / (x1 - x0);
+                const double om = 1.0 - ip_k;
+                c0 += ((double)pl[0] * om + (double)pr[0] * ip_k) * significance;
+                c1 += ((double)pl[1] * om + (double)pr[1] * ip_k) * significance;
+                c2 += ((double)pl[2] * om + (double)pr[2] * ip_k) * significance;
+            }
+            ++i;
+            xi = xn;
+        }
+        dst[3 * col + 0] = f64_to_u8_wrap(c0);
+        dst[3 * col + 1] = f64_to_u8_wrap(c1);
+        dst[3 * col + 2] = f64_to_u8_wrap(c2);
+    }
+    __syncthreads();
+}
+
+__device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px, int fill, uint8_t *dst) {
+    const int tid = threadIdx.x, T_ = blockDim.x;
+    int *winner = sm.off;
+    const bool take_max = div_px < 0.0;  // ascending sweep: the largest source column writes last (:107)
+    for (int c = tid; c < W; c += T_) winner[c] = take_max ? -1 : 0x7fffffff;
+    __syncthreads();
+    for (int col = tid; col < W; col += T_) {
+        const double v = sm.ndp[col] * div_px + sep_px;
+        if (!(v > -4.0e9 && v < 4.0e9)) continue;  // NaN / huge: int() gives INT64_MIN in the reference -> out of range
+        const long long cd = (long long)col + (long long)v;  // int(): truncation toward zero
+        if (cd >= 0 && cd < W) {
+            if (take_max) atomicMax(&winner[(int)cd], col); else atomicMin(&winner[(int)cd], col);
+        }
+    }
+    __syncthreads();
+    // scattered (pre-fill) row -> dst for `none`, -> staging for the fills
+    uint8_t *scat = (fill == DM_FILL_NONE) ? dst : reinterpret_cast<uint8_t *>(sm.pm);
+    for (int c = tid; c < W; c += T_) {
+        const int wsrc = winner[c];
+        const bool f = take_max ? (wsrc >= 0) : (wsrc != 0x7fffffff);
+        uint8_t r = 0, g = 0, b = 0;
+        if (f) { r = sm.src[3 * wsrc]; g = sm.src[3 * wsrc + 1]; b = sm.src[3 * wsrc + 2]; }
+        scat[3 * c] = r; scat[3 * c + 1] = g; scat[3 * c + 2] = b;
+        winner[c] = f ? 1 : 0;  // from here on: the `filled` mask
+    }
+    __syncthreads();
+    if (fill == DM_FILL_NONE) return;
+    const int *filled = winner;
+    if (fill == DM_FILL_NAIVE) {  // :142-157
+        double adp = div_px < 0 ? -div_px : div_px;
+        long long lim = (adp < 4.0e9) ? (long long)adp : 0;  // abs(int(div_px))
+        for (int c = tid; c < W; c += T_) {
+            int from = c;
+            if (!filled[c]) {
+                for (long long o = 1; o < lim + 2; ++o) {
+                    const long long ro = c + o, lo = c - o;
+                    if (ro < W && filled[ro]) { from = (int)ro; break; }
+                    if (lo >= 0 && filled[lo]) { from = (int)lo; break; }
+                    if (ro >= W && lo < 0) break;
+                }
+            }
+            dst[3 * c] = scat[3 * from]; dst[3 * c + 1] = scat[3 * from + 1]; dst[3 * c + 2] = scat[3 * from + 2];
+        }
+        __syncthreads();
+        return;
+    }
+    // naive_interpolating (:114-141) in closed form
+    int *lastV = sm.cur, *nextV = sm.aux, *nextU = sm.off;  // nextU overwrites `filled` after it has been consumed
+    for (int c = tid; c < W; c += T_) {
+        const bool f = filled[c] != 0;
+        const bool nonblack = ((int)scat[3 * c] + scat[3 * c + 1] + scat[3 * c + 2]) != 0;
+        const bool V = f && nonblack;
+        lastV[c] = V ? c : -1;
+        nextV[c] = V ? c : W;
+    }
+    __syncthreads();
+    for (int c = tid; c < W; c += T_) nextU[c] = filled[c] ? W : c;  // same thread reads and writes element c
+    __syncthreads();
+    block_scan_inclusive<int>(lastV, W, -1, OpMaxI(), false, sm.wtot_i);
+    block_scan_inclusive<int>(nextV, W, W, OpMinI(), true, sm.wtot_i);
+    block_scan_inclusive<int>(nextU, W, W, OpMinI(), true, sm.wtot_i);
+    for (int p = tid; p < W; p += T_) {
+        const int v = lastV[p];
+        const int l = (v + 1 < W) ? nextU[v + 1] : W;
+        uint8_t o0 = scat[3 * p], o1 = scat[3 * p + 1], o2 = scat[3 * p + 2];
+        if (l <= p) {
+            const int r = nextV[p];  // p itself is not V here
+            int lb[3] = {0, 0, 0}, rb[3] = {0, 0, 0};
+            if (l > 0) { lb[0] = scat[3 * (l - 1)]; lb[1] = scat[3 * (l - 1) + 1]; lb[2] = scat[3 * (l - 1) + 2]; }
+            if (r < W) { rb[0] = scat[3 * r]; rb[1] = scat[3 * r + 1]; rb[2] = scat[3 * r + 2]; }
+            if (lb[0] + lb[1] + lb[2] == 0) { lb[0] = rb[0]; lb[1] = rb[1]; lb[2] = rb[2]; }
+            else if (rb[0] + rb[1] + rb[2] == 0) { rb[0] = lb[0]; rb[1] = lb[1]; rb[2] = lb[2]; }
+            const double total_steps = (double)(1 + r - l);
+            const double k = (double)(p - l + 1);
+            o0 = (uint8_t)(lb[0] + f64_to_u8_wrap(((double)rb[0] - (double)lb[0]) / total_steps * k));
+            o1 = (uint8_t)(lb[1] + f64_to_u8_wrap(((double)rb[1] - (double)lb[1]) / total_steps * k));
+            o2 = (uint8_t)(lb[2] + f64_to_u8_wrap(((double)rb[2] - (double)lb[2]) / total_steps * k));
+        }
+        dst[3 * p] = o0; dst[3 * p + 1] = o1; dst[3 * p + 2] = o2;
+    }
+    __syncthreads();
+}
+
+__global__ void stereo_row_kernel(StereoArgs a, int pow_kind) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int W = a.W, y = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, T_ = blockDim.x;
+    const bool poly = a.fill == DM_FILL_POLYLINES_SOFT || a.fill == DM_FILL_POLYLINES_SHARP;
+    const int n = a.fill == DM_FILL_POLYLINES_SHARP ? 2 * W + 2 : W + 2;
+
+    RowSmem sm;
+    size_t o = 0;
+    auto carve = [&](size_t bytes) { uint8_t *p = smem_raw + o; o += (bytes + 15) & ~(size_t)15; return p; };
+    sm.wtot_d = (double *)carve(32 * sizeof(double));
+    sm.wtot_i = (int *)carve(32 * sizeof(int));
+    sm.ndp = (double *)carve(sizeof(double) * W);
+    sm.pm = (double *)carve(poly ? sizeof(double) * n : (size_t)3 * W);
+    sm.off = (int *)carve(sizeof(int) * (W + 3));
+    sm.cur = (int *)carve(sizeof(int) * (W + 3));
+    sm.aux = (int *)carve(a.fill == DM_FILL_NAIVE_INTERPOLATING ? sizeof(int) * (W + 1) : 16);
+    sm.order = (uint16_t *)carve(poly ? sizeof(uint16_t) * n : 16);
+    sm.src = carve((size_t)3 * W);
+    sm.eye[0] = carve((size_t)3 * W);
+    sm.eye[1] = carve((size_t)3 * W);
+
+    // ---- load the row: RGB bytes and nd ** exponent --------------------------------------------------------
+    const uint8_t *src_g = a.rgb + ((int64_t)b * a.H + y) * (int64_t)W * 3;
+    {
+        const int nbytes = 3 * W;
+        const int head = (int)((16 - ((uintptr_t)src_g & 15)) & 15);
+        const int h = head < nbytes ? head : nbytes;
+        for (int i = tid; i < h; i += T_) sm.src[i] = __ldg(src_g + i);
+        const int nvec = (nbytes - h) >> 4;
+        for (int i = tid; i < nvec; i += T_) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src_g + h) + i);
+            uint8_t *d = sm.src + h + i * 16;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { d[4 * k] = w[k] & 0xff; d[4 * k + 1] = (w[k] >> 8) & 0xff; d[4 * k + 2] = (w[k] >> 16) & 0xff; d[4 * k + 3] = w[k] >> 24; }
+        }
+        for (int i = h + nvec * 16 + tid; i < nbytes; i += T_) sm.src[i] = __ldg(src_g + i);
+    }
+    bool flat = false;
+    if (a.depth_kind == DM_DEPTH_U16) {
+        const uint16_t *dep = (const uint16_t *)a.depth + ((int64_t)b * a.H + y) * (int64_t)W;
+        const uint32_t mn = a.minmax[2 * b], mx = a.minmax[2 * b + 1];
+        flat = (mx == mn);
+        const double den = (double)(mx - mn);
+        for (int c = tid; c < W; c += T_) {
+            const double nd = (double)((uint32_t)__ldg(dep + c) - mn) / den;   // :81, float64 true-divide
+            sm.ndp[c] = pow_ref(nd, a.exponent, pow_kind);
+        }
+    } else {
+        const double *dep = (const double *)a.depth + ((int64_t)b * a.H + y) * (int64_t)W;
+        for (int c = tid; c < W; c += T_) sm.ndp[c] = pow_ref(__ldg(dep + c), a.exponent, pow_kind);
+    }
+    __syncthreads();
+
+    // ---- eyes ---------------------------------------------------------------------------------------------------
+    for (int e = 0; e < 2; ++e) {
+        if (a.eye_mode[e] == DM_EYE_SKIP) continue;
+        uint8_t *dst = sm.eye[e];
+        if (a.eye_mode[e] == DM_EYE_IDENTITY) {
+            for (int i = tid; i < 3 * W; i += T_) dst[i] = sm.src[i];
+            __syncthreads();
+        } else if (flat) {
+            // max == min: nd is 0/0 = NaN everywhere.  Reference behaviour (pinned by the oracle): the naive family
+            // scatters nothing (black row); polylines degenerates to the first pixel's colour across the row.
+            for (int c = tid; c < W; c += T_)
+                for (int k = 0; k < 3; ++k) dst[3 * c + k] = poly ? sm.src[k] : (uint8_t)0;
+            __syncthreads();
+        } else if (a.fill == DM_FILL_POLYLINES_SHARP) {
+            polylines_eye<true>(sm, W, a.div_px[e], a.sep_px[e], dst);
+        } else if (a.fill == DM_FILL_POLYLINES_SOFT) {
+            polylines_eye<false>(sm, W, a.div_px[e], a.sep_px[e], dst);
+        } else {
+            naive_eye(sm, W, a.div_px[e], a.sep_px[e], a.fill, dst);
+        }
+    }
+
+    // ---- pack + store -------------------------------------------------------------------------------------------
+    if (a.pack == DM_PACK_ANAGLYPH) {
+        const uint8_t *er = sm.eye[a.red_eye], *ec = sm.eye[1 - a.red_eye];
+        uint8_t *comp = sm.src;
+        __syncthreads();
+        for (int c = tid; c < W; c += T_) { comp[3 * c] = er[3 * c]; comp[3 * c + 1] = ec[3 * c + 1]; comp[3 * c + 2] = ec[3 * c + 2]; }
+        __syncthreads();
+        store_row(a.out[0] + (int64_t)b * a.img_stride[0] + (int64_t)y * a.row_stride[0], comp, 3 * W);
+    } else {
+        for (int e = 0; e < 2; ++e) {
+            if (a.eye_mode[e] == DM_EYE_SKIP || !a.out[e]) continue;
+            store_row(a.out[e] + (int64_t)b * a.img_stride[e] + (int64_t)y * a.row_stride[e], sm.eye[e], 3 * W);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) minmax_u16_kernel(const uint16_t *__restrict__ depth, int64_t n, uint32_t *ws) {
+    const int b = blockIdx.y;
+    const uint16_t *p = depth + (int64_t)b * n;
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = (n % 8 == 0) && (((uintptr_t)depth) % 16 == 0);
+    if (vec) {
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
+        for (int64_t i = tid; i < n / 8; i += nthreads) {
+            const uint4 v = __ldg(p4 + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t a0 = w[k] & 0xffffu, a1 = w[k] >> 16;
+                lo = min(lo, min(a0, a1)); hi = max(hi, max(a0, a1));
+            }
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += nthreads) { const uint32_t v = __ldg(p + i); lo = min(lo, v); hi = max(hi, v); }
+    }
+    lo = warp_min_u32(lo); hi = warp_max_u32(hi);
+    __shared__ uint32_t slo[8], shi[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { slo[warp] = lo; shi[warp] = hi; }
+    __syncthreads();
+    if (warp == 0) {
+        lo = lane < 8 ? slo[lane] : 0xffffffffu; hi = lane < 8 ? shi[lane] : 0u;
+        lo = warp_min_u32(lo); hi = warp_max_u32(hi);
+        if (lane == 0) { atomicMin(ws + 2 * b, lo); atomicMax(ws + 2 * b + 1, hi); }
+    }
+}
+
+__global__ void minmax_u16_init_kernel(uint32_t *ws, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { ws[2 * i] = 0xffffffffu; ws[2 * i + 1] = 0u; }
+}
+
+static size_t stereo_smem_bytes(int W, int fill) {
+    const bool poly = fill == DM_FILL_POLYLINES_SOFT || fill == DM_FILL_POLYLINES_SHARP;
+    const size_t n = fill == DM_FILL_POLYLINES_SHARP ? 2 * (size_t)W + 2 : (size_t)W + 2;
+    auto r16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t s = r16(32 * 8) + r16(32 * 4) + r16(8 * (size_t)W) + r16(poly ? 8 * n : 3 * (size_t)W) + 2 * r16(4 * ((size_t)W + 3)) +
+               r16(fill == DM_FILL_NAIVE_INTERPOLATING ? 4 * ((size_t)W + 1) : 16) + r16(poly ? 2 * n : 16) + 3 * r16(3 * (size_t)W);
+    return s;
+}
+
+}  // namespace dm
+
+extern "C" __attribute__((visibility("default"))) size_t dm_stereo_workspace_bytes(int B, int H, int W) {
+    (void)H; (void)W;
+    return dm::align_up((size_t)(B > 0 ? B : 1) * 2 * sizeof(uint32_t), 256);
+}
+
+extern "C" __attribute__((visibility("default"))) int dm_stereo(const uint8_t *rgb, const void *depth, int B, int H, int W, const dm_stereo_params *p,
+                         uint8_t *out0, uint8_t *out1, void *workspace, size_t workspace_bytes, void *stream_) {
+    using namespace dm;
+    if (!rgb || !depth || !p || B <= 0 || H <= 0 || W <= 0) { set_error("dm_stereo: bad arguments"); return DM_E_INVALID; }
+    if (p->fill < DM_FILL_NONE || p->fill > DM_FILL_POLYLINES_SHARP) { set_error("dm_stereo: unknown fill %d", p->fill); return DM_E_INVALID; }
+    if (p->pack != DM_PACK_STRIDED && p->pack != DM_PACK_ANAGLYPH) { set_error("dm_stereo: unknown pack %d", p->pack); return DM_E_INVALID; }
+    if (p->depth_kind != DM_DEPTH_U16 && p->depth_kind != DM_DEPTH_ND64) { set_error("dm_stereo: unknown depth_kind"); return DM_E_INVALID; }
+    if (!out0 && (p->pack == DM_PACK_ANAGLYPH || p->eye_mode[0] != DM_EYE_SKIP)) { set_error("dm_stereo: out0 is NULL"); return DM_E_INVALID; }
+    if (p->pack == DM_PACK_STRIDED && !out1 && p->eye_mode[1] != DM_EYE_SKIP) { set_error("dm_stereo: out1 is NULL"); return DM_E_INVALID; }
+    if (p->pack == DM_PACK_ANAGLYPH && (p->eye_mode[0] == DM_EYE_SKIP || p->eye_mode[1] == DM_EYE_SKIP)) { set_error("dm_stereo: anaglyph needs both eyes"); return DM_E_INVALID; }
+    if (H > 2147483647 / 1 || B > 65535) { set_error("dm_stereo: batch too large"); return DM_E_UNSUPPORTED; }
+    if (W > 32000) { set_error("dm_stereo: rows wider than 32000 px are not supported"); return DM_E_UNSUPPORTED; }
+    if (!workspace || workspace_bytes < dm_stereo_workspace_bytes(B, H, W)) { set_error("dm_stereo: workspace too small"); return DM_E_WORKSPACE; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    uint32_t *ws = (uint32_t *)workspace;
+
+    const size_t smem = stereo_smem_bytes(W, p->fill);
+    if (smem > 227 * 1024) {
+        set_error("dm_stereo: a %d px row needs %zu B of shared memory (> 227 KB); image too wide for this fill mode", W, smem);
+        return DM_E_UNSUPPORTED;
+    }
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        DM_CUDA_CHECK(cudaFuncSetAttribute(stereo_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = 227 * 1024;
+    }
+    if (p->depth_kind == DM_DEPTH_U16) {
+        const int64_t n = (int64_t)H * W;
+        minmax_u16_init_kernel<<<(B + 255) / 256, 256, 0, stream>>>(ws, B);
+        DM_LAUNCH_CHECK("minmax_u16_init_kernel");
+        int bx = (int)((n / 8 + 255) / 256);
+        bx = bx < 1 ? 1 : (bx > 148 * 4 ? 148 * 4 : bx);
+        minmax_u16_kernel<<<dim3(bx, B), 256, 0, stream>>>((const uint16_t *)depth, n, ws);
+        DM_LAUNCH_CHECK("minmax_u16_kernel");
+    }
+    StereoArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rgb = rgb; a.depth = depth; a.minmax = ws; a.H = H; a.W = W; a.exponent = p->exponent;
+    for (int e = 0; e < 2; ++e) {
+        a.div_px[e] = p->div_px[e]; a.sep_px[e] = p->sep_px[e]; a.eye_mode[e] = p->eye_mode[e];
+        a.row_stride[e] = p->dst_row_stride[e]; a.img_stride[e] = p->dst_img_stride[e];
+    }
+    a.fill = p->fill; a.pack = p->pack; a.red_eye = p->anaglyph_red_eye ? 1 : 0; a.depth_kind = p->depth_kind;
+    a.out[0] = out0; a.out[1] = out1;
+    const int pow_kind = p->exponent == 1.0 ? 0 : (p->exponent == 2.0 ? 1 : 2);
+    const int threads = W <= 256 ? 128 : (W <= 1024 ? 256 : 512);
+    stereo_row_kernel<<<dim3(H, B), threads, smem, stream>>>(a, pow_kind);
+    DM_LAUNCH_CHECK("stereo_row_kernel");
+    return DM_OK;
+}
