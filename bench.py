@@ -188,9 +188,7 @@ def run_reference(args, rank, world):
     wl_cls = WORKLOADS[args.workload]
     wl = wl_cls.__new__(wl_cls)
     cores = os.cpu_count() or 1
-    if hasattr(wl_cls, "reference_arm"):
-        line = wl_cls.reference_arm(args, cores)
-    else:
+    if True:
         import torch
         rgb, pred = make_images(1, wl_cls.H, wl_cls.W, 0)
         wl.rgb_h, wl.pred_h = torch.from_numpy(rgb), torch.from_numpy(pred)
@@ -315,6 +313,8 @@ def main():
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e}}
         if kernel_ms is not None:
             line["roofline"] = wl.roofline(peaks, kernel_ms)
+        if hasattr(wl, "extra"):
+            line.update(wl.extra(ms_step, peaks))
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()

@@ -93,6 +93,59 @@ size_t dm_normalmap_workspace_bytes(int B, int H, int W, int pre_blur, int sobel
 int dm_normalmap(const uint16_t *depth, int B, int H, int W, int pre_blur, int sobel, int post_blur, int invert,
                  uint8_t *rgb_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * D2-D7 — building blocks of the depth networks (ViT backbone + DPT decoder).  The Python ModelHolder
+ * (stable-diffusion-webui-depthmap-script_b200/depthmap_generation.py) strings these together per model; each call
+ * is one or two kernel launches on `stream`.  fp16 operands, fp32 accumulation, fp32 residual stream.
+ *   replaces: torch nn.Module.forward of DepthAnythingV2 (ddepth_anything_v2/depth_anything_v2/dpt.py:176-184,
+ *   dinov2.py:297-321, dinov2_layers/{attention,block,mlp}.py), DPTDepthModel (dmidas/dpt_depth.py:110-166,
+ *   dmidas/backbones/{beit,utils}.py, dmidas/blocks.py) and the surrounding numpy/cv2 pre/post-processing
+ *   (dpt.py:196-221, src/depthmap_generation.py:455-499,548-559).
+ * ------------------------------------------------------------------------------------------------------------- */
+enum { DM_EPI_STORE_F16 = 0, DM_EPI_RESID_F32 = 1, DM_EPI_PIXSHUF = 2, DM_EPI_HEAD = 3, DM_EPI_STORE_F32 = 4 };
+enum { DM_ACT_NONE = 0, DM_ACT_GELU = 1, DM_ACT_RELU = 2 };
+
+/* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (tcgen05 tensor cores, TMA-fed).  K % 64 == 0, N % 32 == 0. */
+typedef struct dm_gemm_desc {
+    int32_t M, N, K;
+    int32_t epi, act;        /* DM_EPI_*, DM_ACT_* */
+    const float *bias;       /* [N] fp32 or NULL */
+    void *C; int32_t ldc;    /* fp16 output (STORE_F16 / PIXSHUF) */
+    void *C2;                /* optional relu(C) copy, same layout */
+    const void *R; int32_t ldr;    /* optional fp16 residual added before the store */
+    const void *R2; int32_t ldr2;  /* optional second fp16 residual */
+    float *X; int32_t ldx;   /* fp32 residual stream (RESID_F32: X += gamma*(acc+bias)) or fp32 output (STORE_F32 / HEAD) */
+    const float *gamma;      /* [N] LayerScale (RESID_F32) or the fused 1x1 head weights (HEAD) */
+    float head_b2;           /* HEAD: bias of the fused 1x1 conv */
+    int32_t ps_s, ps_cout, ps_h, ps_w;  /* PIXSHUF: ConvTranspose2d(kernel = stride = ps_s) scatter geometry */
+} dm_gemm_desc;
+
+int dm_gemm_ex(const void *A, int lda, const void *W, int ldw, const dm_gemm_desc *desc_host, void *stream);
+/* 3x3 stride-1 pad-1 conv as implicit GEMM: act NHWC fp16 [B,H,W,Cin], Wt fp16 [Cout, 9*Cin] ordered (ky,kx,cin);
+ * desc->N = Cout; M and K are derived. */
+int dm_conv3x3_ex(const void *act, int B, int H, int W, int Cin, const void *Wt, const dm_gemm_desc *desc_host, void *stream);
+/* convenience wrappers used by the unit tests */
+int dm_gemm_f16(const void *A, int lda, const void *W, int ldw, const float *bias, void *C, int ldc, int M, int N, int K,
+                int act, int out_f32, void *stream);
+int dm_conv3x3_f16(const void *act, int B, int H, int W, int Cin, const void *Wt, const float *bias, void *out, int Cout,
+                   int relu, void *stream);
+/* softmax(scale * Q K^T [+ bias]) V for head_dim 64 straight from the packed qkv activation [B*N, 3*H*64] (fp16);
+ * bias: optional fp16 [H, N, bias_ld]; out: fp16 [B*N, H*64]. */
+int dm_attention_f16(const void *qkv, int B, int N, int H, float scale, const void *bias, int bias_ld, void *out, void *stream);
+/* uint8 RGB [B,H,W,3] -> (cv2-style bicubic resize to net_h x net_w) -> (x/255 - mean)/std -> fp16 patch matrix
+ * [B*(net_h/patch)*(net_w/patch), kpad], K ordered (c, ky, kx); network channel c reads source channel chan_map[c]. */
+int dm_preprocess_patchify(const uint8_t *rgb, int B, int H, int W, int net_h, int net_w, int patch, const float *mean_host,
+                           const float *std_host, const int *chan_map_host, void *out, int kpad, void *stream);
+/* X[b,0,:] = cls + pos[0]; X[b,1+p,:] = pe[b*Np+p,:] + pos[1+p]  (pos may be NULL); X fp32 [B, Np+1, C] */
+int dm_assemble_tokens(const void *pe, const float *cls, const float *pos, float *X, int B, int Np, int C, void *stream);
+/* LayerNorm over the last dim of fp32 x [rows, C] -> fp16; drop_first != 0 skips token 0 of every image (tokens_per_img) */
+int dm_layernorm_f16(const float *x, long long rows, int C, const float *gamma, const float *beta, float eps, void *out,
+                     int tokens_per_img, int drop_first, void *stream);
+int dm_resize_bilinear_nhwc_f16(const void *in, int B, int Hin, int Win, int C, void *out, int Hout, int Wout, void *stream);
+/* mode 0: bilinear align_corners=True; mode 1: bicubic align_corners=False */
+int dm_resize_f32(const float *in, int B, int Hin, int Win, float *out, int Hout, int Wout, int mode, void *stream);
+int dm_im2col_s2_f16(const void *in, int B, int H, int W, int C, void *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

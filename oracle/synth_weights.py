@@ -1,0 +1,140 @@
+"""ORACLE / TEST + BENCH DATA.  Seeded synthetic state_dicts in the reference's checkpoint layout.
+
+No checkpoint is reachable offline, and default-initialised DA-v2 weights give an identically-zero output after the
+trailing ReLUs, so fixtures use a scaled random init that keeps activations O(1) through 24 blocks and
+the decoder and yields a non-degenerate, strictly varying depth.  Key names and shapes are exactly those of
+DepthAnythingV2(**cfg).state_dict() (checked with strict load in tests/test_oracle_pin.py).
+"""
+from __future__ import annotations
+
+import torch
+
+from .dav2 import CONFIGS
+
+
+def make_dav2_state_dict(encoder='vits', seed=0, num_pos=37 * 37 + 1, dtype=torch.float32):
+    cfg = CONFIGS[encoder]
+    C, depth, Fch, oc = cfg['embed_dim'], cfg['depth'], cfg['features'], cfg['out_channels']
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=1.0, mean=0.0):
+        return (torch.randn(*shape, generator=g) * std + mean).to(dtype)
+
+    sd = {}
+    sd['pretrained.cls_token'] = rn(1, 1, C, std=0.02)
+    sd['pretrained.pos_embed'] = rn(1, num_pos, C, std=0.1)
+    sd['pretrained.mask_token'] = torch.zeros(1, C, dtype=dtype)
+    sd['pretrained.patch_embed.proj.weight'] = rn(C, 3, 14, 14, std=(1.0 / 588) ** 0.5)
+    sd['pretrained.patch_embed.proj.bias'] = rn(C, std=0.02)
+    for i in range(depth):
+        p = f'pretrained.blocks.{i}.'
+        sd[p + 'norm1.weight'] = rn(C, std=0.05, mean=1.0)
+        sd[p + 'norm1.bias'] = rn(C, std=0.02)
+        sd[p + 'attn.qkv.weight'] = rn(3 * C, C, std=C ** -0.5)
+        sd[p + 'attn.qkv.bias'] = rn(3 * C, std=0.02)
+        sd[p + 'attn.proj.weight'] = rn(C, C, std=C ** -0.5)
+        sd[p + 'attn.proj.bias'] = rn(C, std=0.02)
+        sd[p + 'ls1.gamma'] = rn(C, std=0.02, mean=0.2)
+        sd[p + 'norm2.weight'] = rn(C, std=0.05, mean=1.0)
+        sd[p + 'norm2.bias'] = rn(C, std=0.02)
+        sd[p + 'mlp.fc1.weight'] = rn(4 * C, C, std=C ** -0.5)
+        sd[p + 'mlp.fc1.bias'] = rn(4 * C, std=0.02)
+        sd[p + 'mlp.fc2.weight'] = rn(C, 4 * C, std=(4 * C) ** -0.5)
+        sd[p + 'mlp.fc2.bias'] = rn(C, std=0.02)
+        sd[p + 'ls2.gamma'] = rn(C, std=0.02, mean=0.2)
+    sd['pretrained.norm.weight'] = rn(C, std=0.05, mean=1.0)
+    sd['pretrained.norm.bias'] = rn(C, std=0.02)
+
+    h = 'depth_head.'
+    for i in range(4):
+        sd[h + f'projects.{i}.weight'] = rn(oc[i], C, 1, 1, std=C ** -0.5)
+        sd[h + f'projects.{i}.bias'] = rn(oc[i], std=0.02)
+    sd[h + 'resize_layers.0.weight'] = rn(oc[0], oc[0], 4, 4, std=oc[0] ** -0.5)
+    sd[h + 'resize_layers.0.bias'] = rn(oc[0], std=0.02)
+    sd[h + 'resize_layers.1.weight'] = rn(oc[1], oc[1], 2, 2, std=oc[1] ** -0.5)
+    sd[h + 'resize_layers.1.bias'] = rn(oc[1], std=0.02)
+    sd[h + 'resize_layers.3.weight'] = rn(oc[3], oc[3], 3, 3, std=(9 * oc[3]) ** -0.5)
+    sd[h + 'resize_layers.3.bias'] = rn(oc[3], std=0.02)
+    for i in range(4):
+        sd[h + f'scratch.layer{i + 1}_rn.weight'] = rn(Fch, oc[i], 3, 3, std=(9 * oc[i]) ** -0.5)
+    for i in range(1, 5):
+        r = h + f'scratch.refinenet{i}.'
+        sd[r + 'out_conv.weight'] = rn(Fch, Fch, 1, 1, std=Fch ** -0.5)
+        sd[r + 'out_conv.bias'] = rn(Fch, std=0.02)
+        for u in ('resConfUnit1', 'resConfUnit2'):
+            for cv in ('conv1', 'conv2'):
+                sd[r + f'{u}.{cv}.weight'] = rn(Fch, Fch, 3, 3, std=(2.0 / (9 * Fch)) ** 0.5 * 0.7)
+                sd[r + f'{u}.{cv}.bias'] = rn(Fch, std=0.02)
+    sd[h + 'scratch.output_conv1.weight'] = rn(Fch // 2, Fch, 3, 3, std=(9 * Fch) ** -0.5)
+    sd[h + 'scratch.output_conv1.bias'] = rn(Fch // 2, std=0.02)
+    sd[h + 'scratch.output_conv2.0.weight'] = rn(32, Fch // 2, 3, 3, std=(2.0 / (9 * (Fch // 2))) ** 0.5)
+    sd[h + 'scratch.output_conv2.0.bias'] = rn(32, std=0.05, mean=0.1)
+    sd[h + 'scratch.output_conv2.2.weight'] = rn(1, 32, 1, 1, std=0.08, mean=0.05)
+    sd[h + 'scratch.output_conv2.2.bias'] = torch.full((1,), 0.5, dtype=dtype)
+    return sd
+
+
+def make_beit_dpt_state_dict(name='beit_tiny', seed=0, dtype=torch.float32):
+    """Seeded synthetic state_dict in the layout of the MiDaS 3.1 checkpoints (dpt_beit_large_512.pt): keys
+    `pretrained.model.*` (timm Beit), `pretrained.act_postprocess{1..4}.*`, `scratch.*`."""
+    from .beit_dpt import CONFIGS as BCFG
+    cfg = BCFG[name]
+    C, depth, heads, Fch, oc, win = cfg['embed_dim'], cfg['depth'], cfg['heads'], cfg['features'], cfg['out_channels'], cfg['window']
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=1.0, mean=0.0):
+        return (torch.randn(*shape, generator=g) * std + mean).to(dtype)
+
+    sd = {}
+    p = 'pretrained.model.'
+    sd[p + 'cls_token'] = rn(1, 1, C, std=0.5)
+    sd[p + 'patch_embed.proj.weight'] = rn(C, 3, 16, 16, std=(1.0 / 768) ** 0.5 * 2.0)
+    sd[p + 'patch_embed.proj.bias'] = rn(C, std=0.02)
+    nrd = (2 * win - 1) * (2 * win - 1) + 3
+    for i in range(depth):
+        b = p + f'blocks.{i}.'
+        sd[b + 'gamma_1'] = rn(C, std=0.02, mean=0.2)
+        sd[b + 'gamma_2'] = rn(C, std=0.02, mean=0.2)
+        sd[b + 'norm1.weight'] = rn(C, std=0.05, mean=1.0)
+        sd[b + 'norm1.bias'] = rn(C, std=0.02)
+        sd[b + 'attn.q_bias'] = rn(C, std=0.02)
+        sd[b + 'attn.v_bias'] = rn(C, std=0.02)
+        sd[b + 'attn.relative_position_bias_table'] = rn(nrd, heads, std=1.0)
+        sd[b + 'attn.qkv.weight'] = rn(3 * C, C, std=C ** -0.5)
+        sd[b + 'attn.proj.weight'] = rn(C, C, std=C ** -0.5)
+        sd[b + 'attn.proj.bias'] = rn(C, std=0.02)
+        sd[b + 'norm2.weight'] = rn(C, std=0.05, mean=1.0)
+        sd[b + 'norm2.bias'] = rn(C, std=0.02)
+        sd[b + 'mlp.fc1.weight'] = rn(4 * C, C, std=C ** -0.5)
+        sd[b + 'mlp.fc1.bias'] = rn(4 * C, std=0.02)
+        sd[b + 'mlp.fc2.weight'] = rn(C, 4 * C, std=(4 * C) ** -0.5)
+        sd[b + 'mlp.fc2.bias'] = rn(C, std=0.02)
+    for j in range(1, 5):
+        a = f'pretrained.act_postprocess{j}.'
+        sd[a + '0.project.0.weight'] = rn(C, 2 * C, std=(2 * C) ** -0.5)
+        sd[a + '0.project.0.bias'] = rn(C, std=0.02)
+        sd[a + '3.weight'] = rn(oc[j - 1], C, 1, 1, std=C ** -0.5 * 1.5)
+        sd[a + '3.bias'] = rn(oc[j - 1], std=0.02)
+    sd['pretrained.act_postprocess1.4.weight'] = rn(oc[0], oc[0], 4, 4, std=oc[0] ** -0.5)
+    sd['pretrained.act_postprocess1.4.bias'] = rn(oc[0], std=0.02)
+    sd['pretrained.act_postprocess2.4.weight'] = rn(oc[1], oc[1], 2, 2, std=oc[1] ** -0.5)
+    sd['pretrained.act_postprocess2.4.bias'] = rn(oc[1], std=0.02)
+    sd['pretrained.act_postprocess4.4.weight'] = rn(oc[3], oc[3], 3, 3, std=(9 * oc[3]) ** -0.5)
+    sd['pretrained.act_postprocess4.4.bias'] = rn(oc[3], std=0.02)
+    for i in range(4):
+        sd[f'scratch.layer{i + 1}_rn.weight'] = rn(Fch, oc[i], 3, 3, std=(9 * oc[i]) ** -0.5)
+    for i in range(1, 5):
+        r = f'scratch.refinenet{i}.'
+        sd[r + 'out_conv.weight'] = rn(Fch, Fch, 1, 1, std=Fch ** -0.5)
+        sd[r + 'out_conv.bias'] = rn(Fch, std=0.02)
+        for u in ('resConfUnit1', 'resConfUnit2'):
+            for cv in ('conv1', 'conv2'):
+                sd[r + f'{u}.{cv}.weight'] = rn(Fch, Fch, 3, 3, std=(2.0 / (9 * Fch)) ** 0.5 * 0.7)
+                sd[r + f'{u}.{cv}.bias'] = rn(Fch, std=0.02)
+    sd['scratch.output_conv.0.weight'] = rn(Fch // 2, Fch, 3, 3, std=(9 * Fch) ** -0.5)
+    sd['scratch.output_conv.0.bias'] = rn(Fch // 2, std=0.02)
+    sd['scratch.output_conv.2.weight'] = rn(32, Fch // 2, 3, 3, std=(2.0 / (9 * (Fch // 2))) ** 0.5)
+    sd['scratch.output_conv.2.bias'] = rn(32, std=0.05, mean=0.1)
+    sd['scratch.output_conv.4.weight'] = rn(1, 32, 1, 1, std=0.08, mean=0.05)
+    sd['scratch.output_conv.4.bias'] = torch.full((1,), 0.5, dtype=dtype)
+    return sd

@@ -6,7 +6,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_native", "libdepthmap_b200.so")
+LIB_PATH = os.environ.get("DEPTHMAP_B200_LIB", os.path.join(_HERE, "_native", "libdepthmap_b200.so"))
 
 DM_OK, DM_E_INVALID, DM_E_CUDA, DM_E_OOM, DM_E_UNSUPPORTED, DM_E_WORKSPACE = 0, -1, -2, -3, -4, -5
 DM_DEPTH_U16, DM_DEPTH_ND64 = 0, 1
@@ -31,6 +31,26 @@ class StereoParams(ctypes.Structure):
     ]
 
 
+class GemmDesc(ctypes.Structure):
+    """mirror of dm_gemm_desc (include/depthmap_b200.h)"""
+    _fields_ = [
+        ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+        ("epi", ctypes.c_int32), ("act", ctypes.c_int32),
+        ("bias", ctypes.c_void_p),
+        ("C", ctypes.c_void_p), ("ldc", ctypes.c_int32),
+        ("C2", ctypes.c_void_p),
+        ("R", ctypes.c_void_p), ("ldr", ctypes.c_int32),
+        ("R2", ctypes.c_void_p), ("ldr2", ctypes.c_int32),
+        ("X", ctypes.c_void_p), ("ldx", ctypes.c_int32),
+        ("gamma", ctypes.c_void_p),
+        ("head_b2", ctypes.c_float),
+        ("ps_s", ctypes.c_int32), ("ps_cout", ctypes.c_int32), ("ps_h", ctypes.c_int32), ("ps_w", ctypes.c_int32),
+    ]
+
+
+EPI_STORE_F16, EPI_RESID_F32, EPI_PIXSHUF, EPI_HEAD, EPI_STORE_F32 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
 _lock = threading.Lock()
 _lib = None
 
@@ -40,6 +60,8 @@ EXPORTS = [
     "dm_normalize_u16_workspace_bytes", "dm_normalize_u16",
     "dm_stereo_workspace_bytes", "dm_stereo",
     "dm_normalmap_workspace_bytes", "dm_normalmap",
+    "dm_gemm_ex", "dm_conv3x3_ex", "dm_gemm_f16", "dm_conv3x3_f16", "dm_attention_f16", "dm_preprocess_patchify",
+    "dm_assemble_tokens", "dm_layernorm_f16", "dm_resize_bilinear_nhwc_f16", "dm_resize_f32", "dm_im2col_s2_f16",
 ]
 
 
@@ -76,8 +98,21 @@ def _bind_optional(L):
     """Model entry points (present once the tensor-core units are linked in)."""
     c = ctypes
     vp, i32, i64, f32, sz = c.c_void_p, c.c_int, c.c_int64, c.c_float, c.c_size_t
-    if hasattr(L, "dm_gemm_bf16"):
-        L.dm_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]
+    if hasattr(L, "dm_gemm_f16"):
+        L.dm_gemm_f16.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+        L.dm_conv3x3_f16.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp]
+        L.dm_gemm_ex.argtypes = [vp, i32, vp, i32, c.POINTER(GemmDesc), vp]
+        L.dm_conv3x3_ex.argtypes = [vp, i32, i32, i32, i32, vp, c.POINTER(GemmDesc), vp]
+    if hasattr(L, "dm_attention_f16"):
+        L.dm_attention_f16.argtypes = [vp, i32, i32, i32, f32, vp, i32, vp, vp]
+    if hasattr(L, "dm_layernorm_f16"):
+        L.dm_preprocess_patchify.argtypes = [vp, i32, i32, i32, i32, i32, i32, c.POINTER(c.c_float), c.POINTER(c.c_float),
+                                             c.POINTER(c.c_int), vp, i32, vp]
+        L.dm_assemble_tokens.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+        L.dm_layernorm_f16.argtypes = [vp, c.c_longlong, i32, vp, vp, f32, vp, i32, i32, vp]
+        L.dm_resize_bilinear_nhwc_f16.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
+        L.dm_resize_f32.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp]
+        L.dm_im2col_s2_f16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
 
 
 def check(rc: int, what: str = ""):

@@ -37,7 +37,7 @@ struct StereoArgs {
     double div_px[2], sep_px[2];
     int eye_mode[2];
     int fill, pack, red_eye, depth_kind;
-    int naive_lim;  // |int(div_px)| per eye is derived on device; kept for clarity
+    double *dbg;    // debug dump (tests only): row 0 / image 0 / first warped eye -> [n, pm[n], order[n], off[W+2]]
     uint8_t *out[2];
     int64_t row_stride[2], img_stride[2];
 };
@@ -145,11 +145,6 @@ struct Poly {
     int W, n;
     double div_px, sep_px;
     const double *ndp;
-    __device__ __forceinline__ int srccol(int t) const {
-        if (t == 0) return 0;
-        if (t == n - 1) return W - 1;
-        return SHARP ? ((t - 1) >> 1) : (t - 1);
-    }
     // :177-192 vertex x in ORIGINAL order
     __device__ __forceinline__ double X(int t) const {
         if (t == 0) return -1.0 * (double)W;
@@ -163,7 +158,7 @@ struct Poly {
 };
 
 template <bool SHARP>
-__device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double sep_px, uint8_t *dst) {
+__device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double sep_px, uint8_t *dst, double *dbg) {
     const int tid = threadIdx.x, T_ = blockDim.x;
     Poly<SHARP> P;
     P.W = W; P.n = SHARP ? 2 * W + 2 : W + 2; P.div_px = div_px; P.sep_px = sep_px; P.ndp = sm.ndp;
@@ -225,6 +220,11 @@ __device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double se
         }
     }
     __syncthreads();
+    if (dbg && tid == 0) {
+        dbg[0] = n;
+        for (int t = 0; t < n; ++t) { dbg[1 + t] = sm.pm[t]; dbg[1 + n + t] = sm.order[t]; dbg[1 + 2 * n + t] = P.X(t); }
+        for (int b = 0; b < W + 2; ++b) dbg[1 + 3 * n + b] = sm.off[b];
+    }
     // 4. rasterise: one output pixel per thread iteration (:228-281)
     for (int col = tid; col < W; col += T_) {
         double c0 = 0.5, c1 = 0.5, c2 = 0.5;
@@ -248,8 +248,14 @@ __device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double se
                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sm.pm[mid] < coord_center) lo = mid; else hi = mid - 1; }
                 s = lo;
             }
-            s = max(0, min(s, n - 2));
-            const int col_l = P.srccol(s), col_r = P.srccol(s + 1);
+            // Source columns of vertices s and s+1.  Written as plain clamps of the column index on purpose: with
+            // CUDA 12.9 ptxas for sm_100a, `s = min(s, n-2)` followed by a test `s == n-2` is fused into a VIMNMX with a
+            // predicate output whose sense is wrong on the hardware (observed: the equality came out true for every
+            // s < n-2), so no equality test may follow a min/max on the same operands here.
+            int col_l = SHARP ? ((s - 1) >> 1) : (s - 1);   // vertex 0 (opening sentinel) -> -1 -> column 0
+            int col_r = SHARP ? (s >> 1) : s;               // vertex n-1 (closing sentinel) -> W -> column W-1
+            col_l = col_l < 0 ? 0 : (col_l > W - 1 ? W - 1 : col_l);
+            col_r = col_r < 0 ? 0 : (col_r > W - 1 ? W - 1 : col_r);
             const uint8_t *pl = sm.src + 3 * col_l;
             if (col_l == col_r) {
                 c0 += (double)pl[0] * significance;
@@ -426,9 +432,9 @@ __global__ void stereo_row_kernel(StereoArgs a, int pow_kind) {
                 for (int k = 0; k < 3; ++k) dst[3 * c + k] = poly ? sm.src[k] : (uint8_t)0;
             __syncthreads();
         } else if (a.fill == DM_FILL_POLYLINES_SHARP) {
-            polylines_eye<true>(sm, W, a.div_px[e], a.sep_px[e], dst);
+            polylines_eye<true>(sm, W, a.div_px[e], a.sep_px[e], dst, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
         } else if (a.fill == DM_FILL_POLYLINES_SOFT) {
-            polylines_eye<false>(sm, W, a.div_px[e], a.sep_px[e], dst);
+            polylines_eye<false>(sm, W, a.div_px[e], a.sep_px[e], dst, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
         } else {
             naive_eye(sm, W, a.div_px[e], a.sep_px[e], a.fill, dst);
         }
@@ -499,6 +505,9 @@ static size_t stereo_smem_bytes(int W, int fill) {
 
 }  // namespace dm
 
+static double *g_stereo_dbg = nullptr;
+extern "C" __attribute__((visibility("default"))) void dm_stereo_set_debug_buffer(double *dev_buf) { g_stereo_dbg = dev_buf; }
+
 extern "C" __attribute__((visibility("default"))) size_t dm_stereo_workspace_bytes(int B, int H, int W) {
     (void)H; (void)W;
     return dm::align_up((size_t)(B > 0 ? B : 1) * 2 * sizeof(uint32_t), 256);
@@ -548,6 +557,7 @@ extern "C" __attribute__((visibility("default"))) int dm_stereo(const uint8_t *r
     }
     a.fill = p->fill; a.pack = p->pack; a.red_eye = p->anaglyph_red_eye ? 1 : 0; a.depth_kind = p->depth_kind;
     a.out[0] = out0; a.out[1] = out1;
+    a.dbg = g_stereo_dbg;
     const int pow_kind = p->exponent == 1.0 ? 0 : (p->exponent == 2.0 ? 1 : 2);
     const int threads = W <= 256 ? 128 : (W <= 1024 ? 256 : 512);
     stereo_row_kernel<<<dim3(H, B), threads, smem, stream>>>(a, pow_kind);

@@ -1,0 +1,516 @@
+"""Depth estimation on B200 — drop-in for the hot-path part of the reference's ``src/depthmap_generation.py``.
+
+``ModelHolder`` keeps the reference's public methods and attributes (src/depthmap_generation.py:40-403):
+``update_settings``, ``ensure_models``, ``load_models``, ``get_default_net_size``, ``offload``, ``reload``,
+``unload_models``, ``get_raw_prediction(input, net_width, net_height) -> (float32 [H,W], invert)``, plus the additive
+``get_raw_prediction_batch`` (uint8 CUDA batch in, float32 CUDA batch out, no host sync) used by the batched funnel and
+the bench.  The network forward is a sequence of C-ABI calls (tcgen05 GEMM / implicit-GEMM conv / fused attention /
+LayerNorm / resize kernels, include/depthmap_b200.h); PyTorch only owns device memory and the stream.
+
+Implemented model types: 12, 13, 14 (Depth-Anything-V2 S/B/L).  Others raise NotImplementedError naming the type.
+Weights: a state_dict in the upstream checkpoint layout (``depth_anything_v2_vit{s,b,l}.pth``), packed once at load
+into the kernels' layout (fp16 GEMM operands, (ky,kx,cin)-ordered conv filters, ConvTranspose as GEMM + pixel shuffle).
+"""
+from __future__ import annotations
+
+import ctypes
+import gc
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+
+DAV2_CONFIGS = {
+    'vits': dict(embed_dim=384, depth=12, heads=6, features=64, out_channels=[48, 96, 192, 384], layers=[2, 5, 8, 11]),
+    'vitb': dict(embed_dim=768, depth=12, heads=12, features=128, out_channels=[96, 192, 384, 768], layers=[2, 5, 8, 11]),
+    'vitl': dict(embed_dim=1024, depth=24, heads=16, features=256, out_channels=[256, 512, 1024, 1024], layers=[4, 11, 17, 23]),
+}
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+def _constrain_to_multiple_of(x, multiple_of, min_val=0, max_val=None):
+    y = int(np.round(x / multiple_of) * multiple_of)
+    if max_val is not None and y > max_val:
+        y = int(np.floor(x / multiple_of) * multiple_of)
+    if y < min_val:
+        y = int(np.ceil(x / multiple_of) * multiple_of)
+    return y
+
+
+def dav2_net_size(width, height, target, multiple_of=14):
+    """Resize(keep_aspect_ratio, lower_bound, multiple of 14) of the reference (util/transform.py:61-104)."""
+    sh, sw = target / height, target / width
+    if sw > sh:
+        sh = sw
+    else:
+        sw = sh
+    return (_constrain_to_multiple_of(sw * width, multiple_of, min_val=target),
+            _constrain_to_multiple_of(sh * height, multiple_of, min_val=target))
+
+
+class _Ops:
+    """Thin typed wrappers over the C-ABI; every method is asynchronous on the current torch stream."""
+
+    def __init__(self):
+        self.L = _lib.load()
+        for name in ("dm_gemm_ex", "dm_conv3x3_ex", "dm_attention_f16", "dm_layernorm_f16"):
+            if not hasattr(self.L, name):
+                raise RuntimeError(f"depthmap_b200: native library lacks {name}; rebuild csrc (no fallback exists)")
+        self.launches = 0
+
+    def gemm(self, A, lda, W, ldw, M, N, K, epi=_lib.EPI_STORE_F16, act=_lib.ACT_NONE, bias=None, C=None, ldc=0, C2=None,
+             R=None, ldr=0, R2=None, ldr2=0, X=None, ldx=0, gamma=None, head_b2=0.0, ps=None):
+        d = _lib.GemmDesc()
+        d.M, d.N, d.K, d.epi, d.act = M, N, K, epi, act
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.C = C.data_ptr() if C is not None else None
+        d.ldc = ldc
+        d.C2 = C2.data_ptr() if C2 is not None else None
+        d.R = R.data_ptr() if R is not None else None
+        d.ldr = ldr
+        d.R2 = R2.data_ptr() if R2 is not None else None
+        d.ldr2 = ldr2
+        d.X = X.data_ptr() if X is not None else None
+        d.ldx = ldx
+        d.gamma = gamma.data_ptr() if gamma is not None else None
+        d.head_b2 = head_b2
+        if ps is not None:
+            d.ps_s, d.ps_cout, d.ps_h, d.ps_w = ps
+        _lib.check(self.L.dm_gemm_ex(A.data_ptr(), lda, W.data_ptr(), ldw, ctypes.byref(d), _lib.stream_ptr()), "dm_gemm_ex")
+        self.launches += 1
+
+    def conv3x3(self, act_t, B, H, W_, Cin, Wt, Cout, epi=_lib.EPI_STORE_F16, act=_lib.ACT_NONE, bias=None, C=None, C2=None,
+                R=None, R2=None, X=None, gamma=None, head_b2=0.0):
+        d = _lib.GemmDesc()
+        d.N, d.epi, d.act = Cout, epi, act
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.C = C.data_ptr() if C is not None else None
+        d.ldc = Cout
+        d.C2 = C2.data_ptr() if C2 is not None else None
+        d.R = R.data_ptr() if R is not None else None
+        d.ldr = Cout
+        d.R2 = R2.data_ptr() if R2 is not None else None
+        d.ldr2 = Cout
+        d.X = X.data_ptr() if X is not None else None
+        d.ldx = 1
+        d.gamma = gamma.data_ptr() if gamma is not None else None
+        d.head_b2 = head_b2
+        _lib.check(self.L.dm_conv3x3_ex(act_t.data_ptr(), B, H, W_, Cin, Wt.data_ptr(), ctypes.byref(d), _lib.stream_ptr()), "dm_conv3x3_ex")
+        self.launches += 1
+
+    def attention(self, qkv, B, N, H, scale, out, bias=None, bias_ld=0):
+        _lib.check(self.L.dm_attention_f16(qkv.data_ptr(), B, N, H, float(scale), bias.data_ptr() if bias is not None else None,
+                                           bias_ld, out.data_ptr(), _lib.stream_ptr()), "dm_attention_f16")
+        self.launches += 1
+
+    def layernorm(self, x, rows, C, w, b, out, tokens_per_img=1, drop_first=0, eps=1e-6):
+        _lib.check(self.L.dm_layernorm_f16(x.data_ptr(), rows, C, w.data_ptr(), b.data_ptr(), eps, out.data_ptr(), tokens_per_img,
+                                           drop_first, _lib.stream_ptr()), "dm_layernorm_f16")
+        self.launches += 1
+
+    def patchify(self, rgb, B, H, W, nh, nw, patch, mean, std, cmap, out, kpad):
+        m = (ctypes.c_float * 3)(*mean)
+        s = (ctypes.c_float * 3)(*std)
+        c = (ctypes.c_int * 3)(*cmap)
+        _lib.check(self.L.dm_preprocess_patchify(rgb.data_ptr(), B, H, W, nh, nw, patch, m, s, c, out.data_ptr(), kpad, _lib.stream_ptr()),
+                   "dm_preprocess_patchify")
+        self.launches += 2 if kpad > 3 * patch * patch else 1
+
+    def tokens(self, pe, cls, pos, X, B, Np, C):
+        _lib.check(self.L.dm_assemble_tokens(pe.data_ptr(), cls.data_ptr(), pos.data_ptr() if pos is not None else None, X.data_ptr(),
+                                             B, Np, C, _lib.stream_ptr()), "dm_assemble_tokens")
+        self.launches += 1
+
+    def resize_nhwc(self, x, B, Hin, Win, C, out, Hout, Wout):
+        _lib.check(self.L.dm_resize_bilinear_nhwc_f16(x.data_ptr(), B, Hin, Win, C, out.data_ptr(), Hout, Wout, _lib.stream_ptr()),
+                   "dm_resize_bilinear_nhwc_f16")
+        self.launches += 1
+
+    def resize_f32(self, x, B, Hin, Win, out, Hout, Wout, mode):
+        _lib.check(self.L.dm_resize_f32(x.data_ptr(), B, Hin, Win, out.data_ptr(), Hout, Wout, mode, _lib.stream_ptr()), "dm_resize_f32")
+        self.launches += 1
+
+    def im2col_s2(self, x, B, H, W, C, out):
+        _lib.check(self.L.dm_im2col_s2_f16(x.data_ptr(), B, H, W, C, out.data_ptr(), _lib.stream_ptr()), "dm_im2col_s2_f16")
+        self.launches += 1
+
+
+def _conv_w(w, cin_pad, cout_pad):
+    """[Cout, Cin, 3, 3] -> fp16 [cout_pad, 9*cin_pad], K ordered (ky, kx, cin)."""
+    import torch
+    co, ci = w.shape[:2]
+    t = torch.zeros(cout_pad, 3, 3, cin_pad, dtype=torch.float16, device=w.device)
+    t[:co, :, :, :ci] = w.permute(0, 2, 3, 1).to(torch.float16)
+    return t.reshape(cout_pad, 9 * cin_pad).contiguous()
+
+
+def _pad_vec(b, n):
+    import torch
+    t = torch.zeros(n, dtype=torch.float32, device=b.device)
+    t[:b.numel()] = b.float().reshape(-1)
+    return t
+
+
+class DepthAnythingV2Engine:
+    """Depth-Anything-V2 (DINOv2 ViT + DPT head) forward on the sm_100a kernels.
+
+    Mirrors DepthAnythingV2.forward / DPTHead.forward / DINOv2.get_intermediate_layers of the reference
+    (ddepth_anything_v2/depth_anything_v2/dpt.py:117-184, dinov2.py:297-321) plus image2tensor (dpt.py:196-221) and the
+    final resize of estimatedepthanything_v2 (src/depthmap_generation.py:548-559)."""
+
+    MEAN = (0.485, 0.456, 0.406)
+    STD = (0.229, 0.224, 0.225)
+    # the reference swaps R/B three times before the network sees the image (src/depthmap_generation.py:381,550; dpt.py:213):
+    # network channel c carries source channel 2-c
+    CHAN_MAP = (2, 1, 0)
+
+    def __init__(self, state_dict, encoder, device):
+        import torch
+        self.cfg = DAV2_CONFIGS[encoder]
+        self.encoder = encoder
+        self.device = device
+        self.ops = _Ops()
+        self._buf_key = None
+        self._bufs = {}
+        self._pos_cache = {}
+        self.probe = None  # bench hook: {'fc1': (start_event, end_event)} records the block-0 fc1 GEMM launch
+        self._pack(state_dict)
+
+    # ---- weight packing --------------------------------------------------------------------------------------------
+    def _pack(self, sd):
+        import torch
+        dev = self.device
+        cfg = self.cfg
+        C, Fch, oc = cfg['embed_dim'], cfg['features'], cfg['out_channels']
+        f16 = lambda t: t.detach().to(dev, torch.float16).contiguous()
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        w = {}
+        pw = sd['pretrained.patch_embed.proj.weight'].detach().to(dev).reshape(C, -1)
+        self.kpad = _ru(pw.shape[1], 64)
+        t = torch.zeros(C, self.kpad, dtype=torch.float16, device=dev)
+        t[:, :pw.shape[1]] = pw.to(torch.float16)
+        w['pe_w'], w['pe_b'] = t, f32(sd['pretrained.patch_embed.proj.bias'])
+        w['cls'] = f32(sd['pretrained.cls_token']).reshape(C)
+        self._pos_embed = f32(sd['pretrained.pos_embed'])
+        blocks = []
+        for i in range(cfg['depth']):
+            p = f'pretrained.blocks.{i}.'
+            blocks.append(dict(
+                ln1_w=f32(sd[p + 'norm1.weight']), ln1_b=f32(sd[p + 'norm1.bias']),
+                qkv_w=f16(sd[p + 'attn.qkv.weight']), qkv_b=f32(sd[p + 'attn.qkv.bias']),
+                proj_w=f16(sd[p + 'attn.proj.weight']), proj_b=f32(sd[p + 'attn.proj.bias']), ls1=f32(sd[p + 'ls1.gamma']),
+                ln2_w=f32(sd[p + 'norm2.weight']), ln2_b=f32(sd[p + 'norm2.bias']),
+                fc1_w=f16(sd[p + 'mlp.fc1.weight']), fc1_b=f32(sd[p + 'mlp.fc1.bias']),
+                fc2_w=f16(sd[p + 'mlp.fc2.weight']), fc2_b=f32(sd[p + 'mlp.fc2.bias']), ls2=f32(sd[p + 'ls2.gamma'])))
+        w['blocks'] = blocks
+        w['norm_w'], w['norm_b'] = f32(sd['pretrained.norm.weight']), f32(sd['pretrained.norm.bias'])
+        # ---- DPT head; channel counts padded to multiples of 64 with zero weights (ViT-S/B have 48/96-wide maps) ----
+        self.ocp = [_ru(c, 64) for c in oc]
+        self.Fp = _ru(Fch, 64)
+        self.F2p = _ru(Fch // 2, 64)
+        h = 'depth_head.'
+        for i in range(4):
+            t = torch.zeros(self.ocp[i], C, dtype=torch.float16, device=dev)
+            t[:oc[i]] = sd[h + f'projects.{i}.weight'].detach().to(dev).reshape(oc[i], C).to(torch.float16)
+            w[f'proj{i}_w'], w[f'proj{i}_b'] = t, _pad_vec(sd[h + f'projects.{i}.bias'].detach().to(dev), self.ocp[i])
+        for i, s in ((0, 4), (1, 2)):  # ConvTranspose2d(k = s): W[(i,j,co), ci] = w[ci, co, i, j]
+            wt = sd[h + f'resize_layers.{i}.weight'].detach().to(dev)  # [ci, co, s, s]
+            t = torch.zeros(s, s, self.ocp[i], self.ocp[i], dtype=torch.float16, device=dev)
+            t[:, :, :oc[i], :oc[i]] = wt.permute(2, 3, 1, 0).to(torch.float16)
+            w[f'up{i}_w'] = t.reshape(s * s * self.ocp[i], self.ocp[i]).contiguous()
+            w[f'up{i}_b'] = _pad_vec(sd[h + f'resize_layers.{i}.bias'].detach().to(dev), self.ocp[i]).repeat(s * s).contiguous()
+        w['down3_w'] = _conv_w(sd[h + 'resize_layers.3.weight'].detach().to(dev), self.ocp[3], self.ocp[3])
+        w['down3_b'] = _pad_vec(sd[h + 'resize_layers.3.bias'].detach().to(dev), self.ocp[3])
+        for i in range(4):
+            w[f'rn{i}_w'] = _conv_w(sd[h + f'scratch.layer{i + 1}_rn.weight'].detach().to(dev), self.ocp[i], self.Fp)
+        for i in range(1, 5):
+            r = h + f'scratch.refinenet{i}.'
+            t = torch.zeros(self.Fp, self.Fp, dtype=torch.float16, device=dev)
+            t[:Fch, :Fch] = sd[r + 'out_conv.weight'].detach().to(dev).reshape(Fch, Fch).to(torch.float16)
+            w[f'rf{i}_out_w'], w[f'rf{i}_out_b'] = t, _pad_vec(sd[r + 'out_conv.bias'].detach().to(dev), self.Fp)
+            for u in (1, 2):
+                for cv in (1, 2):
+                    k = r + f'resConfUnit{u}.conv{cv}.'
+                    if k + 'weight' in sd:
+                        w[f'rf{i}_u{u}c{cv}_w'] = _conv_w(sd[k + 'weight'].detach().to(dev), self.Fp, self.Fp)
+                        w[f'rf{i}_u{u}c{cv}_b'] = _pad_vec(sd[k + 'bias'].detach().to(dev), self.Fp)
+        w['oc1_w'] = _conv_w(sd[h + 'scratch.output_conv1.weight'].detach().to(dev), self.Fp, self.F2p)
+        w['oc1_b'] = _pad_vec(sd[h + 'scratch.output_conv1.bias'].detach().to(dev), self.F2p)
+        w['oc2_w'] = _conv_w(sd[h + 'scratch.output_conv2.0.weight'].detach().to(dev), self.F2p, 32)
+        w['oc2_b'] = f32(sd[h + 'scratch.output_conv2.0.bias'])
+        w['oc3_w'] = f32(sd[h + 'scratch.output_conv2.2.weight']).reshape(32)
+        self.oc3_b = float(sd[h + 'scratch.output_conv2.2.bias'].detach().float().reshape(-1)[0])
+        self.w = w
+
+    def _pos(self, gh, gw):
+        """interpolate_pos_encoding (dinov2.py:179-210); identity for the native 37x37 grid.  Setup-time, cached."""
+        import torch
+        import torch.nn.functional as F
+        key = (gh, gw)
+        if key in self._pos_cache:
+            return self._pos_cache[key]
+        pe = self._pos_embed
+        C = pe.shape[-1]
+        N = pe.shape[1] - 1
+        if gh * gw == N and gh == gw:
+            out = pe.reshape(N + 1, C).contiguous()
+        else:
+            sqrt_n = math.sqrt(N)
+            # the reference hands (w, h) = (tensor H, tensor W) to the function: "w0" follows the tensor height
+            w0, h0 = gh + 0.1, gw + 0.1
+            pp = F.interpolate(pe[:, 1:].reshape(1, int(sqrt_n), int(sqrt_n), C).permute(0, 3, 1, 2),
+                               scale_factor=(float(w0) / sqrt_n, float(h0) / sqrt_n), mode="bicubic", antialias=False)
+            assert pp.shape[-2] == gh and pp.shape[-1] == gw
+            out = torch.cat((pe[:, 0], pp.permute(0, 2, 3, 1).reshape(-1, C)), dim=0).contiguous()
+        self._pos_cache[key] = out
+        return out
+
+    # ---- activation buffers ----------------------------------------------------------------------------------------
+    def _buffers(self, B, nh, nw):
+        import torch
+        key = (B, nh, nw)
+        if self._buf_key == key:
+            return self._bufs
+        self._bufs = {}
+        self._buf_key = None
+        dev = self.device
+        C, Fp = self.cfg['embed_dim'], self.Fp
+        gh, gw = nh // 14, nw // 14
+        Np, N = gh * gw, gh * gw + 1
+        h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
+        b = {}
+        b['patches'] = h16(B * Np, self.kpad)
+        b['pe'] = h16(B * Np, C)
+        b['x'] = torch.empty(B * N, C, dtype=torch.float32, device=dev)
+        b['h'] = h16(B * N, C)
+        b['qkv'] = h16(B * N, 3 * C)
+        b['att'] = h16(B * N, C)
+        b['mlp'] = h16(B * N, 4 * C)
+        b['feat'] = [h16(B * Np, C) for _ in range(4)]
+        sizes = [(gh * 4, gw * 4), (gh * 2, gw * 2), (gh, gw), ((gh - 1) // 2 + 1, (gw - 1) // 2 + 1)]
+        b['sizes'] = sizes
+        b['p'] = [h16(B * Np, self.ocp[i]) for i in range(4)]
+        b['r'] = [h16(B, sizes[0][0], sizes[0][1], self.ocp[0]), h16(B, sizes[1][0], sizes[1][1], self.ocp[1]), None,
+                  h16(B, sizes[3][0], sizes[3][1], self.ocp[3])]
+        b['cols3'] = h16(B * sizes[3][0] * sizes[3][1], 9 * self.ocp[3])
+        b['l'] = [h16(B, s[0], s[1], Fp) for s in sizes]
+        b['lr'] = [h16(B, s[0], s[1], Fp) for s in sizes]
+        for i in range(4):
+            s = sizes[i]
+            b[f't{i}'] = h16(B, s[0], s[1], Fp)      # relu(conv1(.)) scratch
+            b[f'o{i}'] = h16(B, s[0], s[1], Fp)      # fused sum
+            b[f'or{i}'] = h16(B, s[0], s[1], Fp)     # relu copy
+            b[f'u{i}'] = h16(B, s[0], s[1], Fp)      # RCU2 output
+        up = [sizes[2], sizes[1], sizes[0], (sizes[0][0] * 2, sizes[0][1] * 2)]  # target size of refinenet4..1
+        b['up_sizes'] = up
+        b['v'] = [h16(B, s[0], s[1], Fp) for s in up]      # interpolated
+        b['path'] = [h16(B, s[0], s[1], Fp) for s in up]   # after out_conv
+        b['oc1'] = h16(B, up[3][0], up[3][1], self.F2p)
+        b['oc1u'] = h16(B, nh, nw, self.F2p)
+        b['d'] = torch.empty(B, nh, nw, dtype=torch.float32, device=dev)
+        self._bufs, self._buf_key = b, key
+        return b
+
+    # ---- forward ---------------------------------------------------------------------------------------------------
+    def forward_batch(self, rgb, net_size, out_hw=None):
+        """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] raw prediction (what estimatedepthanything_v2 returns)."""
+        import torch
+        ops, w, cfg = self.ops, self.w, self.cfg
+        B, H, W, _ = rgb.shape
+        nw, nh = dav2_net_size(W, H, net_size)
+        C, heads, Fp = cfg['embed_dim'], cfg['heads'], self.Fp
+        gh, gw = nh // 14, nw // 14
+        Np, N = gh * gw, gh * gw + 1
+        b = self._buffers(B, nh, nw)
+        E, A = _lib, _lib
+        # image2tensor + patch embedding + tokens
+        ops.patchify(rgb, B, H, W, nh, nw, 14, self.MEAN, self.STD, self.CHAN_MAP, b['patches'], self.kpad)
+        ops.gemm(b['patches'], self.kpad, w['pe_w'], self.kpad, B * Np, C, self.kpad, bias=w['pe_b'], C=b['pe'], ldc=C)
+        ops.tokens(b['pe'], w['cls'], self._pos(gh, gw), b['x'], B, Np, C)
+        rows = B * N
+        fi = 0
+        for i, blk in enumerate(w['blocks']):
+            ops.layernorm(b['x'], rows, C, blk['ln1_w'], blk['ln1_b'], b['h'])
+            ops.gemm(b['h'], C, blk['qkv_w'], C, rows, 3 * C, C, bias=blk['qkv_b'], C=b['qkv'], ldc=3 * C)
+            ops.attention(b['qkv'], B, N, heads, (C // heads) ** -0.5, b['att'])
+            ops.gemm(b['att'], C, blk['proj_w'], C, rows, C, C, epi=E.EPI_RESID_F32, bias=blk['proj_b'], X=b['x'], ldx=C, gamma=blk['ls1'])
+            ops.layernorm(b['x'], rows, C, blk['ln2_w'], blk['ln2_b'], b['h'])
+            if self.probe is not None and i == 0:
+                self.probe['fc1'][0].record()
+            ops.gemm(b['h'], C, blk['fc1_w'], C, rows, 4 * C, C, act=A.ACT_GELU, bias=blk['fc1_b'], C=b['mlp'], ldc=4 * C)
+            if self.probe is not None and i == 0:
+                self.probe['fc1'][1].record()
+            ops.gemm(b['mlp'], 4 * C, blk['fc2_w'], 4 * C, rows, C, 4 * C, epi=E.EPI_RESID_F32, bias=blk['fc2_b'], X=b['x'], ldx=C, gamma=blk['ls2'])
+            if i in cfg['layers']:
+                ops.layernorm(b['x'], rows, C, w['norm_w'], w['norm_b'], b['feat'][fi], tokens_per_img=N, drop_first=1)
+                fi += 1
+        # ---- DPT head (dpt.py:117-150) ----
+        sizes = b['sizes']
+        for i in range(4):
+            ops.gemm(b['feat'][i], C, w[f'proj{i}_w'], C, B * Np, self.ocp[i], C, bias=w[f'proj{i}_b'], C=b['p'][i], ldc=self.ocp[i])
+        ops.gemm(b['p'][0], self.ocp[0], w['up0_w'], self.ocp[0], B * Np, 16 * self.ocp[0], self.ocp[0], epi=E.EPI_PIXSHUF, bias=w['up0_b'],
+                 C=b['r'][0], ps=(4, self.ocp[0], gh, gw))
+        ops.gemm(b['p'][1], self.ocp[1], w['up1_w'], self.ocp[1], B * Np, 4 * self.ocp[1], self.ocp[1], epi=E.EPI_PIXSHUF, bias=w['up1_b'],
+                 C=b['r'][1], ps=(2, self.ocp[1], gh, gw))
+        r2 = b['p'][2]
+        ops.im2col_s2(b['p'][3], B, gh, gw, self.ocp[3], b['cols3'])
+        ops.gemm(b['cols3'], 9 * self.ocp[3], w['down3_w'], 9 * self.ocp[3], B * sizes[3][0] * sizes[3][1], self.ocp[3], 9 * self.ocp[3],
+                 bias=w['down3_b'], C=b['r'][3], ldc=self.ocp[3])
+        rs = [b['r'][0], b['r'][1], r2, b['r'][3]]
+        for i in range(4):  # layer{i}_rn (no bias) -> l_i and relu(l_i)
+            ops.conv3x3(rs[i], B, sizes[i][0], sizes[i][1], self.ocp[i], w[f'rn{i}_w'], Fp, C=b['l'][i], C2=b['lr'][i])
+        # refinenet4: resConfUnit2(l4) -> resize -> out_conv
+        s3 = sizes[3]
+        ops.conv3x3(b['lr'][3], B, s3[0], s3[1], Fp, w['rf4_u2c1_w'], Fp, act=A.ACT_RELU, bias=w['rf4_u2c1_b'], C=b['t3'])
+        ops.conv3x3(b['t3'], B, s3[0], s3[1], Fp, w['rf4_u2c2_w'], Fp, bias=w['rf4_u2c2_b'], C=b['u3'], R=b['l'][3])
+        up = b['up_sizes']
+        ops.resize_nhwc(b['u3'], B, s3[0], s3[1], Fp, b['v'][0], up[0][0], up[0][1])
+        ops.gemm(b['v'][0], Fp, w['rf4_out_w'], Fp, B * up[0][0] * up[0][1], Fp, Fp, bias=w['rf4_out_b'], C=b['path'][0], ldc=Fp)
+        # refinenet3, 2, 1: output = path + RCU1(l_i); output = RCU2(output); resize; out_conv
+        for step, (li, rf) in enumerate(((2, 3), (1, 2), (0, 1))):
+            s = sizes[li]
+            path = b['path'][step]
+            ops.conv3x3(b['lr'][li], B, s[0], s[1], Fp, w[f'rf{rf}_u1c1_w'], Fp, act=A.ACT_RELU, bias=w[f'rf{rf}_u1c1_b'], C=b[f't{li}'])
+            ops.conv3x3(b[f't{li}'], B, s[0], s[1], Fp, w[f'rf{rf}_u1c2_w'], Fp, bias=w[f'rf{rf}_u1c2_b'], C=b[f'o{li}'], C2=b[f'or{li}'],
+                        R=b['l'][li], R2=path)
+            ops.conv3x3(b[f'or{li}'], B, s[0], s[1], Fp, w[f'rf{rf}_u2c1_w'], Fp, act=A.ACT_RELU, bias=w[f'rf{rf}_u2c1_b'], C=b[f't{li}'])
+            ops.conv3x3(b[f't{li}'], B, s[0], s[1], Fp, w[f'rf{rf}_u2c2_w'], Fp, bias=w[f'rf{rf}_u2c2_b'], C=b[f'u{li}'], R=b[f'o{li}'])
+            t = up[step + 1]
+            ops.resize_nhwc(b[f'u{li}'], B, s[0], s[1], Fp, b['v'][step + 1], t[0], t[1])
+            ops.gemm(b['v'][step + 1], Fp, w[f'rf{rf}_out_w'], Fp, B * t[0] * t[1], Fp, Fp, bias=w[f'rf{rf}_out_b'], C=b['path'][step + 1], ldc=Fp)
+        t = up[3]
+        ops.conv3x3(b['path'][3], B, t[0], t[1], Fp, w['oc1_w'], self.F2p, bias=w['oc1_b'], C=b['oc1'])
+        ops.resize_nhwc(b['oc1'], B, t[0], t[1], self.F2p, b['oc1u'], nh, nw)
+        # conv3x3 -> ReLU -> conv1x1 -> ReLU (+ the outer F.relu, idempotent) fused into one epilogue
+        ops.conv3x3(b['oc1u'], B, nh, nw, self.F2p, w['oc2_w'], 32, epi=E.EPI_HEAD, act=A.ACT_RELU, bias=w['oc2_b'], X=b['d'], gamma=w['oc3_w'],
+                    head_b2=self.oc3_b)
+        oh, ow = out_hw if out_hw is not None else (H, W)
+        out = torch.empty(B, oh, ow, dtype=torch.float32, device=self.device)
+        ops.resize_f32(b['d'], B, nh, nw, out, oh, ow, 0)
+        return out
+
+    def to(self, device):
+        return self
+
+
+class ModelHolder:
+    """Same public surface as the reference's ModelHolder (src/depthmap_generation.py:40-403)."""
+
+    def __init__(self):
+        self.depth_model = None
+        self.pix2pix_model = None
+        self.depth_model_type = None
+        self.device = None
+        self.offloaded = False
+        self.resize_mode = None
+        self.normalization = None
+        self.tiling_mode = False
+        # settings injected by update_settings(**ops) in the reference (src/backbone.py:36-49,132-137)
+        self.no_half = False
+        self.precision = "autocast"
+        self.boost_rmax = 1600
+        self.weights_provider = None  # callable(model_type) -> state_dict; default: torch.load of ./models/... like the reference
+
+    def update_settings(self, **kvargs):
+        for k, v in kvargs.items():
+            setattr(self, k, v)
+
+    def ensure_models(self, model_type, device, boost: bool, tiling_mode: bool = False):
+        if model_type == -1 or model_type is None:
+            self.unload_models()
+            return
+        if (model_type != self.depth_model_type or boost != (self.pix2pix_model is not None) or device != self.device or
+                tiling_mode != self.tiling_mode):
+            self.unload_models()
+            self.load_models(model_type, device, boost, tiling_mode)
+        self.reload()
+
+    def load_models(self, model_type, device, boost: bool, tiling_mode: bool = False):
+        """Ensure that the depth model is loaded (reference: src/depthmap_generation.py:76-301)."""
+        import torch
+        _lib.require_cuda()
+        if boost:
+            raise NotImplementedError("BOOST is not implemented in depthmap_b200 yet (SURVEY.md §8 row D9)")
+        if tiling_mode:
+            raise NotImplementedError("tiling_mode (circular conv padding) is not implemented in depthmap_b200 yet")
+        if model_type in (12, 13, 14):
+            letter = {12: 's', 13: 'b', 14: 'l'}[model_type]
+            if self.weights_provider is not None:
+                sd = self.weights_provider(model_type)
+            else:
+                model_path = f"./models/depth_anything_v2/depth_anything_v2_vit{letter}.pth"
+                if not os.path.exists(model_path):
+                    raise FileNotFoundError(f"{model_path} not found (depthmap_b200 does not download checkpoints)")
+                sd = torch.load(model_path, map_location='cpu')
+            model = DepthAnythingV2Engine(sd, f'vit{letter}', torch.device(device))
+        else:
+            raise NotImplementedError(f"model_type {model_type} is not implemented in depthmap_b200 yet "
+                                      f"(implemented: 12, 13, 14 = Depth-Anything-V2 S/B/L)")
+        self.depth_model = model
+        self.depth_model_type = model_type
+        self.resize_mode = "minimal"
+        self.normalization = None
+        self.tiling_mode = tiling_mode
+        self.device = device
+
+    @staticmethod
+    def get_default_net_size(model_type):
+        sizes = {0: [448, 448], 1: [512, 512], 2: [384, 384], 3: [384, 384], 4: [384, 384], 5: [384, 384], 6: [256, 256],
+                 7: [384, 512], 8: [384, 768], 9: [384, 512], 10: [768, 768], 11: [518, 518], 12: [518, 518], 13: [518, 518],
+                 14: [518, 518]}
+        if model_type in sizes:
+            return sizes[model_type]
+        return [512, 512]
+
+    def offload(self):
+        """The reference swaps the model to host RAM between calls to free VRAM for Stable Diffusion (:344-348).
+        Packed weights stay resident on a 180 GB part; the flag is kept so callers observe the same state machine."""
+        if self.device is not None and not self.offloaded:
+            self.offloaded = True
+
+    def reload(self):
+        if self.offloaded:
+            self.offloaded = False
+
+    def move_models_to(self, device):
+        pass
+
+    def unload_models(self):
+        if self.depth_model is not None or self.pix2pix_model is not None:
+            self.depth_model = None
+            self.pix2pix_model = None
+            gc.collect()
+            try:
+                import torch
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
+        self.depth_model_type = None
+        self.device = None
+
+    # ---- prediction ------------------------------------------------------------------------------------------------
+    def get_raw_prediction_batch(self, rgb, net_width, net_height):
+        """uint8 CUDA [B,H,W,3] -> (float32 CUDA [B,H,W], invert flag).  Batched form of get_raw_prediction."""
+        if self.depth_model is None:
+            raise RuntimeError("no depth model loaded; call ensure_models first")
+        if self.depth_model_type in (12, 13, 14):
+            pred = self.depth_model.forward_batch(rgb, net_width)  # estimatedepthanything_v2 passes w as input_size (:552)
+        else:
+            raise NotImplementedError(f"model_type {self.depth_model_type}")
+        return pred, self.depth_model_type in [0, 7, 8, 9, 10]
+
+    def get_raw_prediction(self, input, net_width, net_height):
+        """Get prediction from the model currently loaded by the ModelHolder object (reference :375-403)."""
+        import torch
+        dev = _lib.require_cuda()
+        img = np.asarray(input)
+        if img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
+            img = np.asarray(input.convert('RGB')) if hasattr(input, 'convert') else img
+        t = torch.from_numpy(np.ascontiguousarray(img)).to(dev).unsqueeze(0)
+        pred, invert = self.get_raw_prediction_batch(t, net_width, net_height)
+        return pred[0].cpu().numpy(), invert
