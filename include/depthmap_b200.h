@@ -132,6 +132,11 @@ int dm_conv3x3_f16(const void *act, int B, int H, int W, int Cin, const void *Wt
 /* softmax(scale * Q K^T [+ bias]) V for head_dim 64 straight from the packed qkv activation [B*N, 3*H*64] (fp16);
  * bias: optional fp16 [H, N, bias_ld]; out: fp16 [B*N, H*64]. */
 int dm_attention_f16(const void *qkv, int B, int N, int H, float scale, const void *bias, int bias_ld, void *out, void *stream);
+/* Same, with the BEiT relative-position bias generated on the fly (dmidas/backbones/beit.py:29-62): rel_table_log2e is
+ * fp32 [H, nrd] = the per-head bias table already resized to the gh x gw window, multiplied by log2(e);
+ * nrd = (2gh-1)(2gw-1)+3, N = gh*gw+1 tokens (class token first).  No [H,N,N] bias tensor is materialised. */
+int dm_attention_relpos_f16(const void *qkv, int B, int gh, int gw, int H, float scale, const float *rel_table_log2e, int nrd,
+                            void *out, void *stream);
 /* uint8 RGB [B,H,W,3] -> (cv2-style bicubic resize to net_h x net_w) -> (x/255 - mean)/std -> fp16 patch matrix
  * [B*(net_h/patch)*(net_w/patch), kpad], K ordered (c, ky, kx); network channel c reads source channel chan_map[c]. */
 int dm_preprocess_patchify(const uint8_t *rgb, int B, int H, int W, int net_h, int net_w, int patch, const float *mean_host,
@@ -145,6 +150,8 @@ int dm_resize_bilinear_nhwc_f16(const void *in, int B, int Hin, int Win, int C, 
 /* mode 0: bilinear align_corners=True; mode 1: bicubic align_corners=False */
 int dm_resize_f32(const float *in, int B, int Hin, int Win, float *out, int Hout, int Wout, int mode, void *stream);
 int dm_im2col_s2_f16(const void *in, int B, int H, int W, int C, void *out, void *stream);
+/* MiDaS ProjectReadout input: out[b*(N-1)+p, :] = [x[b,1+p,:], x[b,0,:]] (fp32 -> fp16), x fp32 [B, N, C] */
+int dm_concat_readout_f16(const float *x, int B, int N, int C, void *out, void *stream);
 
 #ifdef __cplusplus
 }

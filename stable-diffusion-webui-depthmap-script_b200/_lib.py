@@ -60,8 +60,8 @@ EXPORTS = [
     "dm_normalize_u16_workspace_bytes", "dm_normalize_u16",
     "dm_stereo_workspace_bytes", "dm_stereo",
     "dm_normalmap_workspace_bytes", "dm_normalmap",
-    "dm_gemm_ex", "dm_conv3x3_ex", "dm_gemm_f16", "dm_conv3x3_f16", "dm_attention_f16", "dm_preprocess_patchify",
-    "dm_assemble_tokens", "dm_layernorm_f16", "dm_resize_bilinear_nhwc_f16", "dm_resize_f32", "dm_im2col_s2_f16",
+    "dm_gemm_ex", "dm_conv3x3_ex", "dm_gemm_f16", "dm_conv3x3_f16", "dm_attention_f16", "dm_attention_relpos_f16", "dm_preprocess_patchify",
+    "dm_assemble_tokens", "dm_layernorm_f16", "dm_resize_bilinear_nhwc_f16", "dm_resize_f32", "dm_im2col_s2_f16", "dm_concat_readout_f16",
 ]
 
 
@@ -105,6 +105,7 @@ def _bind_optional(L):
         L.dm_conv3x3_ex.argtypes = [vp, i32, i32, i32, i32, vp, c.POINTER(GemmDesc), vp]
     if hasattr(L, "dm_attention_f16"):
         L.dm_attention_f16.argtypes = [vp, i32, i32, i32, f32, vp, i32, vp, vp]
+        L.dm_attention_relpos_f16.argtypes = [vp, i32, i32, i32, i32, f32, vp, i32, vp, vp]
     if hasattr(L, "dm_layernorm_f16"):
         L.dm_preprocess_patchify.argtypes = [vp, i32, i32, i32, i32, i32, i32, c.POINTER(c.c_float), c.POINTER(c.c_float),
                                              c.POINTER(c.c_int), vp, i32, vp]
@@ -113,6 +114,7 @@ def _bind_optional(L):
         L.dm_resize_bilinear_nhwc_f16.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
         L.dm_resize_f32.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp]
         L.dm_im2col_s2_f16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+        L.dm_concat_readout_f16.argtypes = [vp, i32, i32, i32, vp, vp]
 
 
 def check(rc: int, what: str = ""):

@@ -14,6 +14,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -53,110 +54,37 @@ struct GemmCfg {
     static constexpr int STAGES = BN >= 256 ? 3 : (BN == 128 ? 3 : 4);
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGING_BYTES = 4 * 4096;   // one 32x32 fp32 transpose buffer per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/;   // base is __align__(1024)
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): two MUFU ops + a handful of FMAs instead of erff's long polynomial,
+// so the GELU epilogue of the fc1 GEMM stays hidden behind the next tile's MMAs.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t, ex;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * z * -1.4426950408889634f));   // exp(-z^2)
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = fmaf(-poly * t, ex, 1.0f);           // erf(|x|/sqrt2)
+    const float hx = 0.5f * x;
+    return fmaf(fabsf(hx), e, hx);                       // 0.5 x (1 + sign(x) e) = hx + |hx| e
+}
 
-template <int BN, bool CONV>
-__global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-    using Cfg = GemmCfg<BN>;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t *empty = full + Cfg::STAGES;
-    uint64_t *tmem_full = empty + Cfg::STAGES;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, n_blk = blockIdx.y;
-    const int num_kb = CONV ? 9 * (p.cCin / Cfg::BK) : p.K / Cfg::BK;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmA);
-        prefetch_tmap(&tmB);
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    // conv tile coordinates
-    int cb = 0, cy0 = 0, cx0 = 0;
-    if (CONV) {
-        const int tiles_per_img = p.tiles_x * p.tiles_y;
-        cb = m_blk / tiles_per_img;
-        const int t = m_blk % tiles_per_img;
-        cy0 = (t / p.tiles_x) * p.hbox;
-        cx0 = (t % p.tiles_x) * p.wbox;
-    }
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0, phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t *sa = smem + stage * Cfg::STAGE_BYTES, *sb = sa + Cfg::A_BYTES;
-                mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                if (CONV) {
-                    const int cblks = p.cCin / Cfg::BK;
-                    const int tap = kb / cblks, cblk = kb % cblks;
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    tma_load_4d(sa, &tmA, &full[stage], cblk * Cfg::BK, cx0 + dx, cy0 + dy, cb);
-                } else {
-                    tma_load_2d(sa, &tmA, &full[stage], kb * Cfg::BK, m_blk * Cfg::BM);
-                }
-                tma_load_2d(sb, &tmB, &full[stage], kb * Cfg::BK, n_blk * BN);
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(Cfg::BM, BN, 0, 0, 0);
-            int stage = 0, phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES), sb = sa + Cfg::A_BYTES;
-                const uint64_t adesc = make_desc_kmajor_sw128(sa), bdesc = make_desc_kmajor_sw128(sb);
-#pragma unroll
-                for (int k = 0; k < Cfg::BK / 16; ++k)
-                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                umma_commit(&empty[stage]);
-                if (kb == num_kb - 1) umma_commit(tmem_full);
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else {
-        // ===== epilogue: warps 2..5; TMEM lane quarter = warp % 4 =====
-        const int q = warp & 3;
-        const int row = q * 32 + lane;  // row inside the tile == TMEM lane
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        long long m;      // logical output row
-        bool row_ok;
-        if (CONV) {
-            const int ly = row / p.wbox, lx = row % p.wbox;
-            const int y = cy0 + ly, x = cx0 + lx;
-            row_ok = (y < p.cH) && (x < p.cW);
-            m = ((long long)cb * p.cH + y) * p.cW + x;
-        } else {
-            m = (long long)m_blk * Cfg::BM + row;
-            row_ok = m < p.M;
-        }
+// Epilogue for one accumulator tile: thread owns accumulator row (TMEM lane) `q*32 + lane`, walks BN columns in chunks of 32.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmParams &p, uint32_t tmem_acc, int q, long long m, bool row_ok, int n_base) {
         float head_acc = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             tmem_ld_wait();
-            const int n0 = n_blk * BN + c0;
+            const int n0 = n_base + c0;
             if (!row_ok || n0 >= p.N) continue;
             float v[32];
 #pragma unroll
@@ -247,6 +175,398 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
             }
         }
         if (p.epi == EPI_HEAD && row_ok) p.X[m] = fmaxf(head_acc + p.head_b2, 0.f);
+}
+
+// Coalesced epilogue.  tcgen05.ld hands each thread one accumulator ROW, so storing straight from registers makes
+// every warp-level store touch 32 different cache lines (16 B each).  Instead each warp transposes its 32x32 fp32
+// chunk through a private 4 KB smem buffer (16-byte chunks XOR-swizzled by row, conflict-free both ways) and then
+// 8 lanes cover one row's 128 B, so a warp-level access touches 4 full lines: 8x fewer LSU line transactions for
+// the fp32 residual-stream read-modify-write, 4x fewer for fp16 stores, and fp16 residual reads ride the same pattern.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32_t tmem_acc, int q, int lane, long long m, bool row_ok,
+                                                     int n_base, float *stage, int col_begin = 0, int col_end = BN) {
+    const int sub = lane >> 3, cc = (lane & 7) * 4;
+    const bool has_bias = p.bias != nullptr;
+    // bias (thread = row domain: all 32 columns of the chunk) is prefetched one chunk ahead so its L2 latency hides
+    // behind the previous chunk's work instead of sitting between tcgen05.ld and the first FADD
+    float4 bcur[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bcur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_bias && n_base + col_begin < p.N) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bcur[j] = __ldg(reinterpret_cast<const float4 *>(p.bias + n_base + col_begin + 4 * j));
+    }
+    // the accumulator chunk is software-pipelined as well: chunk c+1 is in flight from TMEM while chunk c is processed
+    uint32_t rn[32];
+    tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col_begin, rn);
+#pragma unroll 1
+    for (int c0 = col_begin; c0 < col_end; c0 += 32) {
+        const int n0 = n_base + c0;
+        const bool col_ok = n0 < p.N;
+        float4 bnext[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bnext[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias && c0 + 32 < col_end && n0 + 32 < p.N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bnext[j] = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + 32 + 4 * j));
+        }
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.epi == EPI_RESID_F32 && col_ok) g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + n0 + cc));
+        uint32_t r[32];
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = rn[j];
+        if (c0 + 32 < col_end) tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32), rn);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[4 * j] = __uint_as_float(r[4 * j]) + bcur[j].x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bcur[j].y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bcur[j].z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bcur[j].w;
+        }
+        if (p.epi == EPI_STORE_F16 || p.epi == EPI_PIXSHUF) {
+            if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (p.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4 *>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        __syncwarp();
+        // pixel-shuffle column mapping is uniform for the chunk
+        int ps_i = 0, ps_j = 0, ps_co = 0;
+        if (p.epi == EPI_PIXSHUF) { const int ij = n0 / p.ps_cout; ps_co = n0 % p.ps_cout; ps_i = ij / p.ps_s; ps_j = ij % p.ps_s; }
+        // ---- transposed domain: 8 lanes cover one row's 128 B; all global loads of the chunk are issued first ----
+        long long m_r[8];
+        bool ok[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = 4 * it + sub;
+            m_r[it] = __shfl_sync(0xffffffffu, m, rr);
+            ok[it] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && col_ok;
+        }
+        if (p.epi == EPI_RESID_F32) {
+            float4 x4[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+                if (ok[it]) x4[it] = *reinterpret_cast<const float4 *>(p.X + m_r[it] * p.ldx + n0 + cc);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = 4 * it + sub;
+                const float4 a = *reinterpret_cast<const float4 *>(stage + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+                if (!ok[it]) continue;
+                float4 x = x4[it];
+                x.x = fmaf(g4.x, a.x, x.x); x.y = fmaf(g4.y, a.y, x.y); x.z = fmaf(g4.z, a.z, x.z); x.w = fmaf(g4.w, a.w, x.w);
+                *reinterpret_cast<float4 *>(p.X + m_r[it] * p.ldx + n0 + cc) = x;
+            }
+        } else if (p.epi == EPI_STORE_F32) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = 4 * it + sub;
+                const float4 a = *reinterpret_cast<const float4 *>(stage + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+                if (ok[it]) *reinterpret_cast<float4 *>(p.X + m_r[it] * p.ldx + n0 + cc) = a;
+            }
+        } else {
+            uint2 r1[8], r2[8];
+            if (p.R) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) if (ok[it]) r1[it] = __ldg(reinterpret_cast<const uint2 *>(p.R + m_r[it] * p.ldr + n0 + cc));
+            }
+            if (p.R2) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) if (ok[it]) r2[it] = __ldg(reinterpret_cast<const uint2 *>(p.R2 + m_r[it] * p.ldr2 + n0 + cc));
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = 4 * it + sub;
+                const float4 a = *reinterpret_cast<const float4 *>(stage + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+                if (!ok[it]) continue;
+                float o0 = a.x, o1 = a.y, o2 = a.z, o3 = a.w;
+                if (p.R) {
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&r1[it].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&r1[it].y));
+                    o0 += f0.x; o1 += f0.y; o2 += f1.x; o3 += f1.y;
+                }
+                if (p.R2) {
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&r2[it].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&r2[it].y));
+                    o0 += f0.x; o1 += f0.y; o2 += f1.x; o3 += f1.y;
+                }
+                __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
+                uint2 u;
+                u.x = *reinterpret_cast<const uint32_t *>(&h0);
+                u.y = *reinterpret_cast<const uint32_t *>(&h1);
+                __half *dst;
+                if (p.epi == EPI_PIXSHUF) {
+                    const int s = p.ps_s;
+                    const long long bb = m_r[it] / ((long long)p.ps_h * p.ps_w);
+                    const int rem = (int)(m_r[it] % ((long long)p.ps_h * p.ps_w));
+                    const int y = rem / p.ps_w, x = rem % p.ps_w;
+                    dst = p.C + (((bb * (p.ps_h * s) + (y * s + ps_i)) * (long long)(p.ps_w * s)) + (x * s + ps_j)) * p.ps_cout + ps_co + cc;
+                } else {
+                    dst = p.C + m_r[it] * p.ldc + n0 + cc;
+                }
+                *reinterpret_cast<uint2 *>(dst) = u;
+                if (p.C2 && p.epi != EPI_PIXSHUF) {
+                    const __half2 z = __float2half2_rn(0.f);
+                    h0 = __hmax2(h0, z); h1 = __hmax2(h1, z);
+                    u.x = *reinterpret_cast<const uint32_t *>(&h0);
+                    u.y = *reinterpret_cast<const uint32_t *>(&h1);
+                    *reinterpret_cast<uint2 *>(p.C2 + m_r[it] * p.ldc + n0 + cc) = u;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bcur[j] = bnext[j];
+    }
+}
+
+template <int BN, bool CONV>
+__global__ void __launch_bounds__(192, 2) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;
+    float *staging = reinterpret_cast<float *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    uint64_t *empty = full + Cfg::STAGES;
+    uint64_t *tmem_full = empty + Cfg::STAGES;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.x, n_blk = blockIdx.y;
+    const int num_kb = CONV ? 9 * (p.cCin / Cfg::BK) : p.K / Cfg::BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // conv tile coordinates
+    int cb = 0, cy0 = 0, cx0 = 0;
+    if (CONV) {
+        const int tiles_per_img = p.tiles_x * p.tiles_y;
+        cb = m_blk / tiles_per_img;
+        const int t = m_blk % tiles_per_img;
+        cy0 = (t / p.tiles_x) * p.hbox;
+        cx0 = (t % p.tiles_x) * p.wbox;
+    }
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t *sa = smem + stage * Cfg::STAGE_BYTES, *sb = sa + Cfg::A_BYTES;
+                mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                if (CONV) {
+                    const int cblks = p.cCin / Cfg::BK;
+                    const int tap = kb / cblks, cblk = kb % cblks;
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    tma_load_4d(sa, &tmA, &full[stage], cblk * Cfg::BK, cx0 + dx, cy0 + dy, cb);
+                } else {
+                    tma_load_2d(sa, &tmA, &full[stage], kb * Cfg::BK, m_blk * Cfg::BM);
+                }
+                tma_load_2d(sb, &tmB, &full[stage], kb * Cfg::BK, n_blk * BN);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(Cfg::BM, BN, 0, 0, 0);
+            int stage = 0, phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES), sb = sa + Cfg::A_BYTES;
+                const uint64_t adesc = make_desc_kmajor_sw128(sa), bdesc = make_desc_kmajor_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < Cfg::BK / 16; ++k)
+                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                umma_commit(&empty[stage]);
+                if (kb == num_kb - 1) umma_commit(tmem_full);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5; TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;  // row inside the tile == TMEM lane
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        long long m;      // logical output row
+        bool row_ok;
+        if (CONV) {
+            const int ly = row / p.wbox, lx = row % p.wbox;
+            const int y = cy0 + ly, x = cx0 + lx;
+            row_ok = (y < p.cH) && (x < p.cW);
+            m = ((long long)cb * p.cH + y) * p.cW + x;
+        } else {
+            m = (long long)m_blk * Cfg::BM + row;
+            row_ok = m < p.M;
+        }
+        if (p.epi == EPI_HEAD) epilogue_rows<BN>(p, tmem_base, q, m, row_ok, n_blk * BN);
+        else epilogue_rows_staged<BN>(p, tmem_base, q, lane, m, row_ok, n_blk * BN, staging + q * 1024);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// tile id -> (m_blk, n_blk).  Tiles are ordered in groups of `group` m-tiles; inside a group all n panels are swept with
+// m fastest.  The CTAs running concurrently therefore share ONE weight panel, and the group's A rows (group x 128 x K
+// fp16, e.g. 148 x 256 KB = 37 MB for K = 1024) stay L2-resident across the n sweep, so A is streamed from HBM once
+// instead of once per n panel (A of the fc1 GEMM at B=64 is 180 MB, larger than the 126 MB L2).
+__device__ __forceinline__ void tile_coords(int tile, int num_m_tiles, int n_tiles, int group, int &m_blk, int &n_blk) {
+    const int per_group = group * n_tiles;
+    const int g = tile / per_group;
+    const int rem = tile - g * per_group;
+    const int m0 = g * group;
+    const int gl = (num_m_tiles - m0) < group ? (num_m_tiles - m0) : group;
+    n_blk = rem / gl;
+    m_blk = m0 + (rem - n_blk * gl);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant for N % 256 == 0: one CTA per SM walks 128 x 256 output tiles (m fastest inside an n panel so the
+// CTAs running concurrently share one weight panel in L2).  UMMA 128x256x16 halves the smem operand traffic per FLOP
+// relative to 128x128 (A 4 KB + B 8 KB per 128 tensor cycles = 96 B/clk, under the 128 B/clk smem port), and two TMEM
+// accumulators (2 x 256 columns = all 512) let the epilogue of tile i overlap the MMAs of tile i+1.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PersistCfg {
+    static constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGING_BYTES = 8 * 4096;   // 8 epilogue warps
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256;
+    static constexpr int TMEM_COLS = 512;
+};
+
+constexpr int PERSIST_THREADS = 64 + 256;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+template <bool CONV>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                     const __grid_constant__ CUtensorMap tmB, GemmParams p,
+                                                                     int num_m_tiles, int num_tiles) {
+    using Cfg = PersistCfg;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;
+    float *staging = reinterpret_cast<float *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    uint64_t *empty = full + Cfg::STAGES;
+    uint64_t *tmem_full = empty + Cfg::STAGES;   // [2]
+    uint64_t *tmem_empty = tmem_full + 2;        // [2]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = CONV ? 9 * (p.cCin / Cfg::BK) : p.K / Cfg::BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 256); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(tile, num_m_tiles, num_tiles / num_m_tiles, (int)gridDim.x, m_blk, n_blk);
+                int cb = 0, cy0 = 0, cx0 = 0;
+                if (CONV) {
+                    const int tiles_per_img = p.tiles_x * p.tiles_y;
+                    cb = m_blk / tiles_per_img;
+                    const int t = m_blk % tiles_per_img;
+                    cy0 = (t / p.tiles_x) * p.hbox;
+                    cx0 = (t % p.tiles_x) * p.wbox;
+                }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *sa = smem + stage * Cfg::STAGE_BYTES, *sb = sa + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    if (CONV) {
+                        const int cblks = p.cCin / Cfg::BK;
+                        const int tap = kb / cblks, cblk = kb % cblks;
+                        tma_load_4d(sa, &tmA, &full[stage], cblk * Cfg::BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full[stage], kb * Cfg::BK, m_blk * Cfg::BM);
+                    }
+                    tma_load_2d(sb, &tmB, &full[stage], kb * Cfg::BK, n_blk * Cfg::BN);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(Cfg::BM, Cfg::BN, 0, 0, 0);
+            int stage = 0, phase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * Cfg::BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES), sb = sa + Cfg::A_BYTES;
+                    const uint64_t adesc = make_desc_kmajor_sw128(sa), bdesc = make_desc_kmajor_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < Cfg::BK / 16; ++k)
+                        umma_f16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware rule); warps 2-5 take columns [0,128), 6-9 [128,256)
+        const int q = warp & 3;
+        const int ehalf = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            int m_blk, n_blk;
+            tile_coords(tile, num_m_tiles, num_tiles / num_m_tiles, (int)gridDim.x, m_blk, n_blk);
+            long long m;
+            bool row_ok;
+            if (CONV) {
+                const int tiles_per_img = p.tiles_x * p.tiles_y;
+                const int cb = m_blk / tiles_per_img;
+                const int t = m_blk % tiles_per_img;
+                const int y = (t / p.tiles_x) * p.hbox + row / p.wbox, x = (t % p.tiles_x) * p.wbox + row % p.wbox;
+                row_ok = (y < p.cH) && (x < p.cW);
+                m = ((long long)cb * p.cH + y) * p.cW + x;
+            } else {
+                m = (long long)m_blk * Cfg::BM + row;
+                row_ok = m < p.M;
+            }
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            epilogue_rows_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
+                                          staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -315,17 +635,50 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gem
 
 static int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32); }
 
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <bool CONV>
+static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_persist_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int n_tiles = p.N / PersistCfg::BN;
+    const int tiles = m_tiles * n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_tcgen05_persist_kernel<CONV><<<grid, PERSIST_THREADS, PersistCfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, tiles);
+    DM_LAUNCH_CHECK("gemm_tcgen05_persist_kernel");
+    return DM_OK;
+}
+
+static bool use_persist(const GemmParams &p, int m_tiles) {
+    static int env = -1;
+    if (env < 0) { const char *e = getenv("DEPTHMAP_B200_NO_PERSIST"); env = (e && e[0] == '1') ? 0 : 1; }
+    return env && p.epi != EPI_HEAD && p.N % 256 == 0 && (long long)m_tiles * (p.N / 256) >= 64;
+}
+
 // Plain GEMM: A fp16 [M, K] (pitch lda), W fp16 [N, K] (pitch ldw)
 int gemm_f16(const __half *A, int lda, const __half *W, int ldw, GemmParams p, cudaStream_t stream) {
     if (p.K % 64 != 0 || p.N % 32 != 0) { set_error("gemm_f16: K must be a multiple of 64 and N of 32 (K=%d N=%d)", p.K, p.N); return DM_E_INVALID; }
     if ((lda % 8) || (ldw % 8)) { set_error("gemm_f16: row pitches must be multiples of 8 elements"); return DM_E_INVALID; }
-    const int bn = (p.epi == EPI_HEAD) ? p.N : pick_bn(p.N);
+    const int m_tiles = (p.M + 127) / 128;
+    const bool persist = use_persist(p, m_tiles);
+    const int bn = persist ? 256 : ((p.epi == EPI_HEAD) ? p.N : pick_bn(p.N));
     CUtensorMap tmA, tmB;
     int rc = make_tmap_2d(&tmA, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda, 128, 64);
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldw, (uint32_t)bn, 64);
     if (rc) return rc;
-    const int m_tiles = (p.M + 127) / 128;
+    if (persist) return launch_persist<false>(tmA, tmB, p, m_tiles, stream);
     switch (bn) {
         case 128: return launch_gemm<128, false>(tmA, tmB, p, m_tiles, stream);
         case 64: return launch_gemm<64, false>(tmA, tmB, p, m_tiles, stream);
@@ -349,13 +702,15 @@ int conv3x3_f16(const __half *act, int B, int H, int W, int Cin, const __half *W
     p.tiles_x = (W + p.wbox - 1) / p.wbox; p.tiles_y = (H + p.hbox - 1) / p.hbox;
     p.cB = B; p.cH = H; p.cW = W; p.cCin = Cin;
     p.M = B * H * W; p.K = 9 * Cin;
-    const int bn = (p.epi == EPI_HEAD) ? p.N : pick_bn(p.N);
+    const int m_tiles = B * p.tiles_x * p.tiles_y;
+    const bool persist = use_persist(p, m_tiles);
+    const int bn = persist ? 256 : ((p.epi == EPI_HEAD) ? p.N : pick_bn(p.N));
     CUtensorMap tmA, tmB;
     int rc = make_tmap_nhwc(&tmA, act, B, H, W, Cin, p.hbox, p.wbox);
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, Wt, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)bn, 64);
     if (rc) return rc;
-    const int m_tiles = B * p.tiles_x * p.tiles_y;
+    if (persist) return launch_persist<true>(tmA, tmB, p, m_tiles, stream);
     switch (bn) {
         case 128: return launch_gemm<128, true>(tmA, tmB, p, m_tiles, stream);
         case 64: return launch_gemm<64, true>(tmA, tmB, p, m_tiles, stream);

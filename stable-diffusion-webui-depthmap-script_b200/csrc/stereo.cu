@@ -127,125 +127,148 @@ __device__ __forceinline__ uint8_t f64_to_u8_wrap(double v) {
 // ---------------------------------------------------------------------------------------------------------------
 // the row kernel
 // ---------------------------------------------------------------------------------------------------------------
+// All row state lives in dynamic shared memory.  The carve-up is kept as BYTE OFFSETS from the file-scope `g_smem`
+// symbol (not as generic pointers inside a struct) so the compiler keeps the shared address space and emits LDS / STS
+// instead of generic LD / ST (the first version's ncu source page showed LD.E / ST.E on every row access).
+extern __shared__ __align__(16) uint8_t g_smem[];
+
 struct RowSmem {
-    uint8_t *src;      // [3W]
-    uint8_t *eye[2];   // [3W] each
-    double *ndp;       // [W]   nd ** exponent
-    double *pm;        // [n]   prefix max / suffix min of vertex x (polylines)
-    uint16_t *order;   // [n]   vertex indices sorted by (x, index) (polylines)
-    int *off;          // [W+3] bucket offsets (polylines) / scratch ints (naive: winner[W])
-    int *cur;          // [W+3] bucket cursors (polylines) / scratch ints (naive_interpolating)
-    int *aux;          // [W+1] naive_interpolating third scan
-    double *wtot_d;    // [32]
-    int *wtot_i;       // [32]
+    uint32_t src;      // u8  [3W]
+    uint32_t eye[2];   // u8  [3W] each
+    uint32_t ndp;      // f64 [W]   nd ** exponent
+    uint32_t xs;       // f64 [n]   vertex x in original order (polylines)
+    uint32_t pm;       // f64 [n]   prefix max / suffix min of vertex x (polylines); u8 [3W] scatter staging (naive)
+    uint32_t order;    // u16 [n]   vertex indices sorted by (x, index) (polylines)
+    uint32_t off;      // i32 [W+3] bucket offsets (polylines) / winner + filled (naive)
+    uint32_t cur;      // i32 [W+3] bucket cursors (polylines) / lastV (naive_interpolating)
+    uint32_t aux;      // i32 [W+1] nextV (naive_interpolating)
+    uint32_t wtot_d;   // f64 [32]
+    uint32_t wtot_i;   // i32 [32]
+    template <typename T>
+    __device__ __forceinline__ T *at(uint32_t o) const { return reinterpret_cast<T *>(g_smem + o); }
 };
 
+// :177-192 vertex x in ORIGINAL order (t = 0 and t = n-1 are the sentinels)
 template <bool SHARP>
-struct Poly {
-    int W, n;
-    double div_px, sep_px;
-    const double *ndp;
-    // :177-192 vertex x in ORIGINAL order
-    __device__ __forceinline__ double X(int t) const {
-        if (t == 0) return -1.0 * (double)W;
-        if (t == n - 1) return 2.0 * (double)W;
-        const int col = SHARP ? ((t - 1) >> 1) : (t - 1);
-        const double coord_d = ndp[col] * div_px;
-        const double coord_x = (double)col + 0.5 + coord_d + sep_px;
-        if (!SHARP) return coord_x;
-        return ((t - 1) & 1) ? coord_x + 0.45 : coord_x - 0.45;
-    }
-};
+__device__ __forceinline__ double vertex_x(int t, int n, int W, const double *ndp, double div_px, double sep_px) {
+    if (t == 0) return -1.0 * (double)W;
+    if (t == n - 1) return 2.0 * (double)W;
+    const int col = SHARP ? ((t - 1) >> 1) : (t - 1);
+    const double coord_d = ndp[col] * div_px;
+    const double coord_x = (double)col + 0.5 + coord_d + sep_px;
+    if (!SHARP) return coord_x;
+    return ((t - 1) & 1) ? coord_x + 0.45 : coord_x - 0.45;
+}
 
 template <bool SHARP>
-__device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double sep_px, uint8_t *dst, double *dbg) {
+__device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double sep_px, uint32_t dst_off, double *dbg) {
     const int tid = threadIdx.x, T_ = blockDim.x;
-    Poly<SHARP> P;
-    P.W = W; P.n = SHARP ? 2 * W + 2 : W + 2; P.div_px = div_px; P.sep_px = sep_px; P.ndp = sm.ndp;
-    const int n = P.n;
+    const int n = SHARP ? 2 * W + 2 : W + 2;
     const bool fwd = !(div_px < 0.0);
+    double *xs = sm.at<double>(sm.xs), *pm = sm.at<double>(sm.pm);
+    const double *ndp = sm.at<double>(sm.ndp);
+    uint16_t *order = sm.at<uint16_t>(sm.order);
+    int *off = sm.at<int>(sm.off), *cur = sm.at<int>(sm.cur);
+    const uint8_t *src = sm.at<uint8_t>(sm.src);
+    uint8_t *dst = sm.at<uint8_t>(dst_off);
 
-    // 1. vertex x, then prefix-max (fwd) or suffix-min (bwd) in original order
-    for (int t = tid; t < n; t += T_) sm.pm[t] = P.X(t);
-    for (int b = tid; b < W + 3; b += T_) sm.off[b] = 0;
+    // 1. vertex x (kept in smem: every later phase reads it), bucket counters
+    for (int t = tid; t < n; t += T_) { const double x = vertex_x<SHARP>(t, n, W, ndp, div_px, sep_px); xs[t] = x; pm[t] = x; }
+    for (int b = tid; b < W + 3; b += T_) off[b] = 0;
     __syncthreads();
     // 2. counting sort by bucket(x): 0 for x<0, 1+floor(x) for 0<=x<W, W+1 for x>=W   (vertices 0..n-2 only, :214)
     for (int t = tid; t < n - 1; t += T_) {
-        const double x = sm.pm[t];
-        int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
-        atomicAdd(&sm.off[b], 1);
+        const double x = xs[t];
+        const int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
+        atomicAdd(&off[b], 1);
     }
     __syncthreads();
-    if (fwd) block_scan_inclusive<double>(sm.pm, n, -INFINITY, OpMaxD(), false, sm.wtot_d);
-    else block_scan_inclusive<double>(sm.pm, n, INFINITY, OpMinD(), true, sm.wtot_d);
-    block_scan_inclusive<int>(sm.off, W + 2, 0, OpAddI(), false, sm.wtot_i);  // inclusive: off[b] = end of bucket b
-    for (int b = tid; b < W + 2; b += T_) sm.cur[b] = b == 0 ? 0 : sm.off[b - 1];
+    if (fwd) block_scan_inclusive<double>(pm, n, -INFINITY, OpMaxD(), false, sm.at<double>(sm.wtot_d));
+    else block_scan_inclusive<double>(pm, n, INFINITY, OpMinD(), true, sm.at<double>(sm.wtot_d));
+    block_scan_inclusive<int>(off, W + 2, 0, OpAddI(), false, sm.at<int>(sm.wtot_i));  // inclusive: off[b] = end of bucket b
+    for (int b = tid; b < W + 2; b += T_) cur[b] = b == 0 ? 0 : off[b - 1];
     __syncthreads();
     for (int t = tid; t < n - 1; t += T_) {
-        const double x = P.X(t);
-        int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
-        const int pos = atomicAdd(&sm.cur[b], 1);
-        sm.order[pos] = (uint16_t)t;
+        const double x = xs[t];
+        const int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
+        order[atomicAdd(&cur[b], 1)] = (uint16_t)t;
     }
-    if (tid == 0) sm.order[n - 1] = (uint16_t)(n - 1);
+    if (tid == 0) order[n - 1] = (uint16_t)(n - 1);
     __syncthreads();
     // 3. order inside buckets by (x, original index)
     for (int b = tid; b < W + 2; b += T_) {
-        const int beg = b == 0 ? 0 : sm.off[b - 1], end = sm.off[b];
+        const int beg = b == 0 ? 0 : off[b - 1], end = off[b];
         if (end - beg < 2) continue;
-        if (b == 0) {  // only its maximum matters (predecessor of pixel 0): move it last
-            int bi = beg; double bx = P.X(sm.order[beg]); int bt = sm.order[beg];
+        if (b == 0 || b == W + 1) {
+            // bucket 0: only its maximum matters (predecessor of pixel 0) -> move it last;
+            // bucket W+1: only its minimum matters (successor of the last in-range vertex) -> move it first
+            const bool want_max = b == 0;
+            int bi = beg, bt = order[beg];
+            double bx = xs[bt];
             for (int i = beg + 1; i < end; ++i) {
-                const int t = sm.order[i]; const double x = P.X(t);
-                if (x > bx || (x == bx && t > bt)) { bx = x; bt = t; bi = i; }
+                const int t = order[i];
+                const double x = xs[t];
+                const bool better = want_max ? (x > bx || (x == bx && t > bt)) : (x < bx || (x == bx && t < bt));
+                if (better) { bx = x; bt = t; bi = i; }
             }
-            const uint16_t tmp = sm.order[end - 1]; sm.order[end - 1] = sm.order[bi]; sm.order[bi] = tmp;
-        } else if (b == W + 1) {  // only its minimum matters (successor of the last in-range vertex): move it first
-            int bi = beg; double bx = P.X(sm.order[beg]); int bt = sm.order[beg];
-            for (int i = beg + 1; i < end; ++i) {
-                const int t = sm.order[i]; const double x = P.X(t);
-                if (x < bx || (x == bx && t < bt)) { bx = x; bt = t; bi = i; }
-            }
-            const uint16_t tmp = sm.order[beg]; sm.order[beg] = sm.order[bi]; sm.order[bi] = tmp;
+            const int slot = want_max ? end - 1 : beg;
+            const uint16_t tmp = order[slot]; order[slot] = order[bi]; order[bi] = tmp;
         } else {
             for (int i = beg + 1; i < end; ++i) {
-                const int t = sm.order[i]; const double x = P.X(t);
+                const int t = order[i];
+                const double x = xs[t];
                 int j = i - 1;
                 while (j >= beg) {
-                    const int tj = sm.order[j]; const double xj = P.X(tj);
-                    if (xj > x || (xj == x && tj > t)) { sm.order[j + 1] = (uint16_t)tj; --j; } else break;
+                    const int tj = order[j];
+                    const double xj = xs[tj];
+                    if (xj > x || (xj == x && tj > t)) { order[j + 1] = (uint16_t)tj; --j; } else break;
                 }
-                sm.order[j + 1] = (uint16_t)t;
+                order[j + 1] = (uint16_t)t;
             }
         }
     }
     __syncthreads();
     if (dbg && tid == 0) {
         dbg[0] = n;
-        for (int t = 0; t < n; ++t) { dbg[1 + t] = sm.pm[t]; dbg[1 + n + t] = sm.order[t]; dbg[1 + 2 * n + t] = P.X(t); }
-        for (int b = 0; b < W + 2; ++b) dbg[1 + 3 * n + b] = sm.off[b];
+        for (int t = 0; t < n; ++t) { dbg[1 + t] = pm[t]; dbg[1 + n + t] = order[t]; dbg[1 + 2 * n + t] = xs[t]; }
+        for (int b = 0; b < W + 2; ++b) dbg[1 + 3 * n + b] = off[b];
     }
     // 4. rasterise: one output pixel per thread iteration (:228-281)
     for (int col = tid; col < W; col += T_) {
         double c0 = 0.5, c1 = 0.5, c2 = 0.5;
-        int i = sm.off[col] - 1;  // last vertex with x < col  (end of bucket `col` == pixels < col)
-        double xi = P.X(sm.order[i]);
+        int i = off[col] - 1;  // last vertex with x < col  (end of bucket `col` == vertices with x < col)
+        int ti = order[i];
+        double xi = xs[ti];
         const double colf = (double)col, colp = (double)(col + 1);
         while (xi < colp) {
-            const double xn = P.X(sm.order[i + 1]);
+            const int tn = order[i + 1];
+            const double xn = xs[tn];
             const double coord_from = (xi > colf ? xi : colf) + EPSILON;
             const double coord_to = (xn < colp ? xn : colp) - EPSILON;
             const double significance = coord_to - coord_from;
             const double coord_center = coord_from + 0.5 * significance;
-            // winning segment s = vertices (s, s+1) in original order
+            // Winning segment s = vertices (s, s+1) in original order.  The left vertex of this sub-interval, ti, is the
+            // natural candidate (exact wherever nothing occludes it); verify against the monotone pm[] and gallop.
             int s;
-            if (fwd) {  // first t with pm[t] >= center
-                int lo = 0, hi = n - 1;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.pm[mid] >= coord_center) hi = mid; else lo = mid + 1; }
-                s = lo - 1;
-            } else {    // last t with pm[t] < center
-                int lo = 0, hi = n - 1;
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sm.pm[mid] < coord_center) lo = mid; else hi = mid - 1; }
+            if (fwd) {   // s + 1 = first t with pm[t] >= center
+                int lo, hi;  // invariant: pm[lo] < center <= pm[hi]  (lo may be -1 conceptually: pm[0] = -W < center)
+                if (pm[ti] >= coord_center) {
+                    hi = ti; lo = ti - 1;
+                    int step = 1;
+                    while (lo > 0 && pm[lo] >= coord_center) { hi = lo; lo -= step; step <<= 1; }
+                    if (lo < 0) lo = 0;
+                } else {
+                    lo = ti; hi = ti + 1;
+                    int step = 1;
+                    while (pm[hi] < coord_center) { lo = hi; hi += step; step <<= 1; if (hi > n - 1) hi = n - 1; }
+                }
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pm[mid] >= coord_center) hi = mid; else lo = mid; }
+                s = hi - 1;
+            } else {     // s = last t with pm[t] < center; pm[ti] <= x_i < center always holds
+                int lo = ti, hi = ti + 1, step = 1;
+                while (hi < n - 1 && pm[hi] < coord_center) { lo = hi; hi += step; step <<= 1; if (hi > n - 1) hi = n - 1; }
+                if (pm[hi] < coord_center) lo = hi;   // cannot happen (pm[n-1] = 2W), kept for safety
+                else while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pm[mid] < coord_center) lo = mid; else hi = mid; }
                 s = lo;
             }
             // Source columns of vertices s and s+1.  Written as plain clamps of the column index on purpose: with
@@ -256,14 +279,14 @@ __device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double se
             int col_r = SHARP ? (s >> 1) : s;               // vertex n-1 (closing sentinel) -> W -> column W-1
             col_l = col_l < 0 ? 0 : (col_l > W - 1 ? W - 1 : col_l);
             col_r = col_r < 0 ? 0 : (col_r > W - 1 ? W - 1 : col_r);
-            const uint8_t *pl = sm.src + 3 * col_l;
+            const uint8_t *pl = src + 3 * col_l;
             if (col_l == col_r) {
                 c0 += (double)pl[0] * significance;
                 c1 += (double)pl[1] * significance;
                 c2 += (double)pl[2] * significance;
             } else {
-                const uint8_t *pr = sm.src + 3 * col_r;
-                const double x0 = P.X(s), x1 = P.X(s + 1);
+                const uint8_t *pr = src + 3 * col_r;
+                const double x0 = xs[s], x1 = xs[s + 1];
                 const double ip_k = (coord_center - x0) / (x1 - x0);
                 const double om = 1.0 - ip_k;
                 c0 += ((double)pl[0] * om + (double)pr[0] * ip_k) * significance;
@@ -271,6 +294,7 @@ __device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double se
                 c2 += ((double)pl[2] * om + (double)pr[2] * ip_k) * significance;
             }
             ++i;
+            ti = tn;
             xi = xn;
         }
         dst[3 * col + 0] = f64_to_u8_wrap(c0);
@@ -280,14 +304,17 @@ __device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double se
     __syncthreads();
 }
 
-__device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px, int fill, uint8_t *dst) {
+__device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px, int fill, uint32_t dst_off) {
     const int tid = threadIdx.x, T_ = blockDim.x;
-    int *winner = sm.off;
+    uint8_t *dst = sm.at<uint8_t>(dst_off);
+    const uint8_t *src = sm.at<uint8_t>(sm.src);
+    const double *ndp = sm.at<double>(sm.ndp);
+    int *winner = sm.at<int>(sm.off);
     const bool take_max = div_px < 0.0;  // ascending sweep: the largest source column writes last (:107)
     for (int c = tid; c < W; c += T_) winner[c] = take_max ? -1 : 0x7fffffff;
     __syncthreads();
     for (int col = tid; col < W; col += T_) {
-        const double v = sm.ndp[col] * div_px + sep_px;
+        const double v = ndp[col] * div_px + sep_px;
         if (!(v > -4.0e9 && v < 4.0e9)) continue;  // NaN / huge: int() gives INT64_MIN in the reference -> out of range
         const long long cd = (long long)col + (long long)v;  // int(): truncation toward zero
         if (cd >= 0 && cd < W) {
@@ -296,12 +323,12 @@ __device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px
     }
     __syncthreads();
     // scattered (pre-fill) row -> dst for `none`, -> staging for the fills
-    uint8_t *scat = (fill == DM_FILL_NONE) ? dst : reinterpret_cast<uint8_t *>(sm.pm);
+    uint8_t *scat = (fill == DM_FILL_NONE) ? dst : sm.at<uint8_t>(sm.pm);
     for (int c = tid; c < W; c += T_) {
         const int wsrc = winner[c];
         const bool f = take_max ? (wsrc >= 0) : (wsrc != 0x7fffffff);
         uint8_t r = 0, g = 0, b = 0;
-        if (f) { r = sm.src[3 * wsrc]; g = sm.src[3 * wsrc + 1]; b = sm.src[3 * wsrc + 2]; }
+        if (f) { r = src[3 * wsrc]; g = src[3 * wsrc + 1]; b = src[3 * wsrc + 2]; }
         scat[3 * c] = r; scat[3 * c + 1] = g; scat[3 * c + 2] = b;
         winner[c] = f ? 1 : 0;  // from here on: the `filled` mask
     }
@@ -327,7 +354,7 @@ __device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px
         return;
     }
     // naive_interpolating (:114-141) in closed form
-    int *lastV = sm.cur, *nextV = sm.aux, *nextU = sm.off;  // nextU overwrites `filled` after it has been consumed
+    int *lastV = sm.at<int>(sm.cur), *nextV = sm.at<int>(sm.aux), *nextU = sm.at<int>(sm.off);  // nextU overwrites `filled` after it has been consumed
     for (int c = tid; c < W; c += T_) {
         const bool f = filled[c] != 0;
         const bool nonblack = ((int)scat[3 * c] + scat[3 * c + 1] + scat[3 * c + 2]) != 0;
@@ -338,9 +365,9 @@ __device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px
     __syncthreads();
     for (int c = tid; c < W; c += T_) nextU[c] = filled[c] ? W : c;  // same thread reads and writes element c
     __syncthreads();
-    block_scan_inclusive<int>(lastV, W, -1, OpMaxI(), false, sm.wtot_i);
-    block_scan_inclusive<int>(nextV, W, W, OpMinI(), true, sm.wtot_i);
-    block_scan_inclusive<int>(nextU, W, W, OpMinI(), true, sm.wtot_i);
+    block_scan_inclusive<int>(lastV, W, -1, OpMaxI(), false, sm.at<int>(sm.wtot_i));
+    block_scan_inclusive<int>(nextV, W, W, OpMinI(), true, sm.at<int>(sm.wtot_i));
+    block_scan_inclusive<int>(nextU, W, W, OpMinI(), true, sm.at<int>(sm.wtot_i));
     for (int p = tid; p < W; p += T_) {
         const int v = lastV[p];
         const int l = (v + 1 < W) ? nextU[v + 1] : W;
@@ -363,27 +390,29 @@ __device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px
     __syncthreads();
 }
 
-__global__ void stereo_row_kernel(StereoArgs a, int pow_kind) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+__global__ void __launch_bounds__(512, 1) stereo_row_kernel(StereoArgs a, int pow_kind) {
     const int W = a.W, y = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, T_ = blockDim.x;
     const bool poly = a.fill == DM_FILL_POLYLINES_SOFT || a.fill == DM_FILL_POLYLINES_SHARP;
     const int n = a.fill == DM_FILL_POLYLINES_SHARP ? 2 * W + 2 : W + 2;
 
     RowSmem sm;
-    size_t o = 0;
-    auto carve = [&](size_t bytes) { uint8_t *p = smem_raw + o; o += (bytes + 15) & ~(size_t)15; return p; };
-    sm.wtot_d = (double *)carve(32 * sizeof(double));
-    sm.wtot_i = (int *)carve(32 * sizeof(int));
-    sm.ndp = (double *)carve(sizeof(double) * W);
-    sm.pm = (double *)carve(poly ? sizeof(double) * n : (size_t)3 * W);
-    sm.off = (int *)carve(sizeof(int) * (W + 3));
-    sm.cur = (int *)carve(sizeof(int) * (W + 3));
-    sm.aux = (int *)carve(a.fill == DM_FILL_NAIVE_INTERPOLATING ? sizeof(int) * (W + 1) : 16);
-    sm.order = (uint16_t *)carve(poly ? sizeof(uint16_t) * n : 16);
+    uint32_t o = 0;
+    auto carve = [&](size_t bytes) { const uint32_t p = o; o += (uint32_t)((bytes + 15) & ~(size_t)15); return p; };
+    sm.wtot_d = carve(32 * sizeof(double));
+    sm.wtot_i = carve(32 * sizeof(int));
+    sm.ndp = carve(sizeof(double) * W);
+    sm.xs = carve(poly ? sizeof(double) * n : 16);
+    sm.pm = carve(poly ? sizeof(double) * n : (size_t)3 * W);
+    sm.off = carve(sizeof(int) * (W + 3));
+    sm.cur = carve(sizeof(int) * (W + 3));
+    sm.aux = carve(a.fill == DM_FILL_NAIVE_INTERPOLATING ? sizeof(int) * (W + 1) : 16);
+    sm.order = carve(poly ? sizeof(uint16_t) * n : 16);
     sm.src = carve((size_t)3 * W);
     sm.eye[0] = carve((size_t)3 * W);
     sm.eye[1] = carve((size_t)3 * W);
+    uint8_t *s_src = sm.at<uint8_t>(sm.src);
+    double *s_ndp = sm.at<double>(sm.ndp);
 
     // ---- load the row: RGB bytes and nd ** exponent --------------------------------------------------------
     const uint8_t *src_g = a.rgb + ((int64_t)b * a.H + y) * (int64_t)W * 3;
@@ -391,16 +420,16 @@ __global__ void stereo_row_kernel(StereoArgs a, int pow_kind) {
         const int nbytes = 3 * W;
         const int head = (int)((16 - ((uintptr_t)src_g & 15)) & 15);
         const int h = head < nbytes ? head : nbytes;
-        for (int i = tid; i < h; i += T_) sm.src[i] = __ldg(src_g + i);
+        for (int i = tid; i < h; i += T_) s_src[i] = __ldg(src_g + i);
         const int nvec = (nbytes - h) >> 4;
         for (int i = tid; i < nvec; i += T_) {
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src_g + h) + i);
-            uint8_t *d = sm.src + h + i * 16;
+            uint8_t *d = s_src + h + i * 16;
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) { d[4 * k] = w[k] & 0xff; d[4 * k + 1] = (w[k] >> 8) & 0xff; d[4 * k + 2] = (w[k] >> 16) & 0xff; d[4 * k + 3] = w[k] >> 24; }
         }
-        for (int i = h + nvec * 16 + tid; i < nbytes; i += T_) sm.src[i] = __ldg(src_g + i);
+        for (int i = h + nvec * 16 + tid; i < nbytes; i += T_) s_src[i] = __ldg(src_g + i);
     }
     bool flat = false;
     if (a.depth_kind == DM_DEPTH_U16) {
@@ -410,40 +439,41 @@ __global__ void stereo_row_kernel(StereoArgs a, int pow_kind) {
         const double den = (double)(mx - mn);
         for (int c = tid; c < W; c += T_) {
             const double nd = (double)((uint32_t)__ldg(dep + c) - mn) / den;   // :81, float64 true-divide
-            sm.ndp[c] = pow_ref(nd, a.exponent, pow_kind);
+            s_ndp[c] = pow_ref(nd, a.exponent, pow_kind);
         }
     } else {
         const double *dep = (const double *)a.depth + ((int64_t)b * a.H + y) * (int64_t)W;
-        for (int c = tid; c < W; c += T_) sm.ndp[c] = pow_ref(__ldg(dep + c), a.exponent, pow_kind);
+        for (int c = tid; c < W; c += T_) s_ndp[c] = pow_ref(__ldg(dep + c), a.exponent, pow_kind);
     }
     __syncthreads();
 
     // ---- eyes ---------------------------------------------------------------------------------------------------
     for (int e = 0; e < 2; ++e) {
         if (a.eye_mode[e] == DM_EYE_SKIP) continue;
-        uint8_t *dst = sm.eye[e];
+        const uint32_t dst_off = e == 0 ? sm.eye[0] : sm.eye[1];
+        uint8_t *dst = sm.at<uint8_t>(dst_off);
         if (a.eye_mode[e] == DM_EYE_IDENTITY) {
-            for (int i = tid; i < 3 * W; i += T_) dst[i] = sm.src[i];
+            for (int i = tid; i < 3 * W; i += T_) dst[i] = s_src[i];
             __syncthreads();
         } else if (flat) {
             // max == min: nd is 0/0 = NaN everywhere.  Reference behaviour (pinned by the oracle): the naive family
             // scatters nothing (black row); polylines degenerates to the first pixel's colour across the row.
             for (int c = tid; c < W; c += T_)
-                for (int k = 0; k < 3; ++k) dst[3 * c + k] = poly ? sm.src[k] : (uint8_t)0;
+                for (int k = 0; k < 3; ++k) dst[3 * c + k] = poly ? s_src[k] : (uint8_t)0;
             __syncthreads();
         } else if (a.fill == DM_FILL_POLYLINES_SHARP) {
-            polylines_eye<true>(sm, W, a.div_px[e], a.sep_px[e], dst, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
+            polylines_eye<true>(sm, W, a.div_px[e], a.sep_px[e], dst_off, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
         } else if (a.fill == DM_FILL_POLYLINES_SOFT) {
-            polylines_eye<false>(sm, W, a.div_px[e], a.sep_px[e], dst, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
+            polylines_eye<false>(sm, W, a.div_px[e], a.sep_px[e], dst_off, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
         } else {
-            naive_eye(sm, W, a.div_px[e], a.sep_px[e], a.fill, dst);
+            naive_eye(sm, W, a.div_px[e], a.sep_px[e], a.fill, dst_off);
         }
     }
 
     // ---- pack + store -------------------------------------------------------------------------------------------
     if (a.pack == DM_PACK_ANAGLYPH) {
-        const uint8_t *er = sm.eye[a.red_eye], *ec = sm.eye[1 - a.red_eye];
-        uint8_t *comp = sm.src;
+        const uint8_t *er = sm.at<uint8_t>(a.red_eye ? sm.eye[1] : sm.eye[0]), *ec = sm.at<uint8_t>(a.red_eye ? sm.eye[0] : sm.eye[1]);
+        uint8_t *comp = s_src;
         __syncthreads();
         for (int c = tid; c < W; c += T_) { comp[3 * c] = er[3 * c]; comp[3 * c + 1] = ec[3 * c + 1]; comp[3 * c + 2] = ec[3 * c + 2]; }
         __syncthreads();
@@ -451,7 +481,7 @@ __global__ void stereo_row_kernel(StereoArgs a, int pow_kind) {
     } else {
         for (int e = 0; e < 2; ++e) {
             if (a.eye_mode[e] == DM_EYE_SKIP || !a.out[e]) continue;
-            store_row(a.out[e] + (int64_t)b * a.img_stride[e] + (int64_t)y * a.row_stride[e], sm.eye[e], 3 * W);
+            store_row(a.out[e] + (int64_t)b * a.img_stride[e] + (int64_t)y * a.row_stride[e], sm.at<uint8_t>(e == 0 ? sm.eye[0] : sm.eye[1]), 3 * W);
         }
     }
 }
@@ -498,7 +528,7 @@ static size_t stereo_smem_bytes(int W, int fill) {
     const bool poly = fill == DM_FILL_POLYLINES_SOFT || fill == DM_FILL_POLYLINES_SHARP;
     const size_t n = fill == DM_FILL_POLYLINES_SHARP ? 2 * (size_t)W + 2 : (size_t)W + 2;
     auto r16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    size_t s = r16(32 * 8) + r16(32 * 4) + r16(8 * (size_t)W) + r16(poly ? 8 * n : 3 * (size_t)W) + 2 * r16(4 * ((size_t)W + 3)) +
+    size_t s = r16(32 * 8) + r16(32 * 4) + r16(8 * (size_t)W) + r16(poly ? 8 * n : 16) + r16(poly ? 8 * n : 3 * (size_t)W) + 2 * r16(4 * ((size_t)W + 3)) +
                r16(fill == DM_FILL_NAIVE_INTERPOLATING ? 4 * ((size_t)W + 1) : 16) + r16(poly ? 2 * n : 16) + 3 * r16(3 * (size_t)W);
     return s;
 }

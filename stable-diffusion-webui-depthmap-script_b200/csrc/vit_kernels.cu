@@ -265,6 +265,25 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const __half *__restrict
     *reinterpret_cast<uint4 *>(out + ((((long long)b * Ho + yo) * Wo + xo) * 9 + tap) * C + c) = v;
 }
 
+// MiDaS ProjectReadout input (dmidas/backbones/utils.py:28-39): row (b, p) = [x[b, 1+p, :], x[b, 0, :]] as fp16
+__global__ void __launch_bounds__(256) concat_readout_kernel(const float *__restrict__ x, int B, int N, int C, __half *__restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 output channels
+    const int c4 = (2 * C) / 4;
+    const long long total = (long long)B * (N - 1) * c4;
+    if (idx >= total) return;
+    const int c = (int)(idx % c4) * 4;
+    const long long row = idx / c4;
+    const int p = (int)(row % (N - 1));
+    const long long b = row / (N - 1);
+    const float *src = c < C ? x + (b * N + 1 + p) * C + c : x + (b * N) * C + (c - C);
+    const float4 v = *reinterpret_cast<const float4 *>(src);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t *>(&h0);
+    u.y = *reinterpret_cast<const uint32_t *>(&h1);
+    *reinterpret_cast<uint2 *>(out + row * (2 * C) + c) = u;
+}
+
 }  // namespace dm
 
 #define DM_EXPORT extern "C" __attribute__((visibility("default")))
@@ -340,5 +359,14 @@ DM_EXPORT int dm_im2col_s2_f16(const void *in, int B, int H, int W, int C, void 
     const long long total = (long long)B * Ho * Wo * 9 * (C / 8);
     im2col_s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)in, B, H, W, C, (__half *)out, Ho, Wo);
     DM_LAUNCH_CHECK("im2col_s2_kernel");
+    return DM_OK;
+}
+
+DM_EXPORT int dm_concat_readout_f16(const float *x, int B, int N, int C, void *out, void *stream_) {
+    using namespace dm;
+    if (C % 4) { set_error("dm_concat_readout_f16: C must be a multiple of 4"); return DM_E_INVALID; }
+    const long long total = (long long)B * (N - 1) * (2 * C / 4);
+    concat_readout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(x, B, N, C, (__half *)out);
+    DM_LAUNCH_CHECK("concat_readout_kernel");
     return DM_OK;
 }

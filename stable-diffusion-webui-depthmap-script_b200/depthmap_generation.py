@@ -7,7 +7,7 @@
 the bench.  The network forward is a sequence of C-ABI calls (tcgen05 GEMM / implicit-GEMM conv / fused attention /
 LayerNorm / resize kernels, include/depthmap_b200.h); PyTorch only owns device memory and the stream.
 
-Implemented model types: 12, 13, 14 (Depth-Anything-V2 S/B/L).  Others raise NotImplementedError naming the type.
+Implemented model types: 1, 2 (MiDaS 3.1 DPT-BEiT-L 512 / 384) and 12, 13, 14 (Depth-Anything-V2 S/B/L).  Others raise NotImplementedError naming the type.
 Weights: a state_dict in the upstream checkpoint layout (``depth_anything_v2_vit{s,b,l}.pth``), packed once at load
 into the kernels' layout (fp16 GEMM operands, (ky,kx,cin)-ordered conv filters, ConvTranspose as GEMM + pixel shuffle).
 """
@@ -108,6 +108,11 @@ class _Ops:
                                            bias_ld, out.data_ptr(), _lib.stream_ptr()), "dm_attention_f16")
         self.launches += 1
 
+    def attention_relpos(self, qkv, B, gh, gw, H, scale, table, nrd, out):
+        _lib.check(self.L.dm_attention_relpos_f16(qkv.data_ptr(), B, gh, gw, H, float(scale), table.data_ptr(), nrd, out.data_ptr(),
+                                                  _lib.stream_ptr()), "dm_attention_relpos_f16")
+        self.launches += 1
+
     def layernorm(self, x, rows, C, w, b, out, tokens_per_img=1, drop_first=0, eps=1e-6):
         _lib.check(self.L.dm_layernorm_f16(x.data_ptr(), rows, C, w.data_ptr(), b.data_ptr(), eps, out.data_ptr(), tokens_per_img,
                                            drop_first, _lib.stream_ptr()), "dm_layernorm_f16")
@@ -161,17 +166,21 @@ class DepthAnythingV2Engine:
 
     Mirrors DepthAnythingV2.forward / DPTHead.forward / DINOv2.get_intermediate_layers of the reference
     (ddepth_anything_v2/depth_anything_v2/dpt.py:117-184, dinov2.py:297-321) plus image2tensor (dpt.py:196-221) and the
-    final resize of estimatedepthanything_v2 (src/depthmap_generation.py:548-559)."""
+    final resize of estimatedepthanything_v2 (src/depthmap_generation.py:548-559).  Also the base of DptBeitEngine: the
+    two families share the ViT block sequence and the whole DPT decoder and differ only in the hooks below."""
 
+    PATCH = 14
     MEAN = (0.485, 0.456, 0.406)
     STD = (0.229, 0.224, 0.225)
     # the reference swaps R/B three times before the network sees the image (src/depthmap_generation.py:381,550; dpt.py:213):
     # network channel c carries source channel 2-c
     CHAN_MAP = (2, 1, 0)
+    FINAL_RESIZE_MODE = 0  # bilinear, align_corners=True (src/depthmap_generation.py:558)
+    CONFIGS = DAV2_CONFIGS
 
     def __init__(self, state_dict, encoder, device):
         import torch
-        self.cfg = DAV2_CONFIGS[encoder]
+        self.cfg = self.CONFIGS[encoder]
         self.encoder = encoder
         self.device = device
         self.ops = _Ops()
@@ -280,7 +289,7 @@ class DepthAnythingV2Engine:
         self._buf_key = None
         dev = self.device
         C, Fp = self.cfg['embed_dim'], self.Fp
-        gh, gw = nh // 14, nw // 14
+        gh, gw = nh // self.PATCH, nw // self.PATCH
         Np, N = gh * gw, gh * gw + 1
         h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
         b = {}
@@ -292,6 +301,7 @@ class DepthAnythingV2Engine:
         b['att'] = h16(B * N, C)
         b['mlp'] = h16(B * N, 4 * C)
         b['feat'] = [h16(B * Np, C) for _ in range(4)]
+        b['cat'] = h16(B * Np, 2 * C) if getattr(self, 'NEEDS_READOUT', False) else None
         sizes = [(gh * 4, gw * 4), (gh * 2, gw * 2), (gh, gw), ((gh - 1) // 2 + 1, (gw - 1) // 2 + 1)]
         b['sizes'] = sizes
         b['p'] = [h16(B * Np, self.ocp[i]) for i in range(4)]
@@ -316,28 +326,40 @@ class DepthAnythingV2Engine:
         self._bufs, self._buf_key = b, key
         return b
 
+    # ---- model-family hooks ------------------------------------------------------------------------------------------
+    def net_size(self, W, H, net_w, net_h):
+        return dav2_net_size(W, H, net_w)  # estimatedepthanything_v2 passes w as input_size (:552)
+
+    def attention(self, i, b, B, N, heads, C, gh, gw):
+        self.ops.attention(b['qkv'], B, N, heads, (C // heads) ** -0.5, b['att'])
+
+    def emit_feature(self, b, fi, B, N, C):
+        """get_intermediate_layers(norm=True) without the class token (dinov2.py:297-321)."""
+        self.ops.layernorm(b['x'], B * N, C, self.w['norm_w'], self.w['norm_b'], b['feat'][fi], tokens_per_img=N, drop_first=1)
+
     # ---- forward ---------------------------------------------------------------------------------------------------
-    def forward_batch(self, rgb, net_size, out_hw=None):
-        """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] raw prediction (what estimatedepthanything_v2 returns)."""
+    def forward_batch(self, rgb, net_w, net_h=None, out_hw=None):
+        """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] raw prediction (what the reference's estimate* returns)."""
         import torch
         ops, w, cfg = self.ops, self.w, self.cfg
         B, H, W, _ = rgb.shape
-        nw, nh = dav2_net_size(W, H, net_size)
+        nw, nh = self.net_size(W, H, net_w, net_h if net_h is not None else net_w)
         C, heads, Fp = cfg['embed_dim'], cfg['heads'], self.Fp
-        gh, gw = nh // 14, nw // 14
+        P_ = self.PATCH
+        gh, gw = nh // P_, nw // P_
         Np, N = gh * gw, gh * gw + 1
         b = self._buffers(B, nh, nw)
         E, A = _lib, _lib
         # image2tensor + patch embedding + tokens
-        ops.patchify(rgb, B, H, W, nh, nw, 14, self.MEAN, self.STD, self.CHAN_MAP, b['patches'], self.kpad)
+        ops.patchify(rgb, B, H, W, nh, nw, P_, self.MEAN, self.STD, self.CHAN_MAP, b['patches'], self.kpad)
         ops.gemm(b['patches'], self.kpad, w['pe_w'], self.kpad, B * Np, C, self.kpad, bias=w['pe_b'], C=b['pe'], ldc=C)
-        ops.tokens(b['pe'], w['cls'], self._pos(gh, gw), b['x'], B, Np, C)
+        ops.tokens(b['pe'], w['cls'], self._pos(gh, gw) if self._pos_embed is not None else None, b['x'], B, Np, C)
         rows = B * N
         fi = 0
         for i, blk in enumerate(w['blocks']):
             ops.layernorm(b['x'], rows, C, blk['ln1_w'], blk['ln1_b'], b['h'])
             ops.gemm(b['h'], C, blk['qkv_w'], C, rows, 3 * C, C, bias=blk['qkv_b'], C=b['qkv'], ldc=3 * C)
-            ops.attention(b['qkv'], B, N, heads, (C // heads) ** -0.5, b['att'])
+            self.attention(i, b, B, N, heads, C, gh, gw)
             ops.gemm(b['att'], C, blk['proj_w'], C, rows, C, C, epi=E.EPI_RESID_F32, bias=blk['proj_b'], X=b['x'], ldx=C, gamma=blk['ls1'])
             ops.layernorm(b['x'], rows, C, blk['ln2_w'], blk['ln2_b'], b['h'])
             if self.probe is not None and i == 0:
@@ -347,7 +369,7 @@ class DepthAnythingV2Engine:
                 self.probe['fc1'][1].record()
             ops.gemm(b['mlp'], 4 * C, blk['fc2_w'], 4 * C, rows, C, 4 * C, epi=E.EPI_RESID_F32, bias=blk['fc2_b'], X=b['x'], ldx=C, gamma=blk['ls2'])
             if i in cfg['layers']:
-                ops.layernorm(b['x'], rows, C, w['norm_w'], w['norm_b'], b['feat'][fi], tokens_per_img=N, drop_first=1)
+                self.emit_feature(b, fi, B, N, C)
                 fi += 1
         # ---- DPT head (dpt.py:117-150) ----
         sizes = b['sizes']
@@ -391,11 +413,148 @@ class DepthAnythingV2Engine:
                     head_b2=self.oc3_b)
         oh, ow = out_hw if out_hw is not None else (H, W)
         out = torch.empty(B, oh, ow, dtype=torch.float32, device=self.device)
-        ops.resize_f32(b['d'], B, nh, nw, out, oh, ow, 0)
+        ops.resize_f32(b['d'], B, nh, nw, out, oh, ow, self.FINAL_RESIZE_MODE)
         return out
 
     def to(self, device):
         return self
+
+BEIT_CONFIGS = {
+    'beitl16_512': dict(embed_dim=1024, depth=24, heads=16, features=256, out_channels=[256, 512, 1024, 1024],
+                        layers=[5, 11, 17, 23], window=32),
+    'beitl16_384': dict(embed_dim=1024, depth=24, heads=16, features=256, out_channels=[256, 512, 1024, 1024],
+                        layers=[5, 11, 17, 23], window=24),
+    'beit_tiny': dict(embed_dim=128, depth=4, heads=2, features=64, out_channels=[64, 64, 128, 128],
+                      layers=[0, 1, 2, 3], window=4),  # structural test configuration
+}
+
+
+def midas_net_size(width, height, net_w, net_h, multiple_of=32):
+    """Resize(keep_aspect_ratio, 'minimal', multiple of 32) of the reference (dmidas/transforms.py:61-104)."""
+    sh, sw = net_h / height, net_w / width
+    if abs(1 - sw) < abs(1 - sh):
+        sh = sw
+    else:
+        sw = sh
+    return _constrain_to_multiple_of(sw * width, multiple_of), _constrain_to_multiple_of(sh * height, multiple_of)
+
+
+def _gen_relative_position_index(wh, ww):
+    """timm 0.9 gen_relative_position_index (restated): cls rows / cols use the three extra table entries."""
+    import torch
+    nrd = (2 * wh - 1) * (2 * ww - 1) + 3
+    coords = torch.stack(torch.meshgrid([torch.arange(wh), torch.arange(ww)], indexing='ij')).flatten(1)
+    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += wh - 1
+    rel[:, :, 1] += ww - 1
+    rel[:, :, 0] *= 2 * ww - 1
+    idx = torch.zeros((wh * ww + 1,) * 2, dtype=rel.dtype)
+    idx[1:, 1:] = rel.sum(-1)
+    idx[0, 0:] = nrd - 3
+    idx[0:, 0] = nrd - 2
+    idx[0, 0] = nrd - 1
+    return idx
+
+
+class DptBeitEngine(DepthAnythingV2Engine):
+    """MiDaS 3.1 DPT-BEiT (dpt_beit_large_512 / _384) on the sm_100a kernels.
+
+    Mirrors the reference's overriding forwards (dmidas/backbones/beit.py:18-129), the reassemble stage
+    (dmidas/backbones/utils.py:28-39,83-124,144-249), DPT / DPTDepthModel (dmidas/dpt_depth.py:110-166) and estimatemidas
+    (src/depthmap_generation.py:455-499).  The relative-position bias, which the reference rebuilds (bilinear table
+    resize + gather) in every block of every forward, is expanded once per resolution into a [heads, N, N] fp16 table
+    per block and added inside the fused attention kernel."""
+
+    PATCH = 16
+    MEAN = (0.5, 0.5, 0.5)
+    STD = (0.5, 0.5, 0.5)
+    CHAN_MAP = (2, 1, 0)        # estimatemidas receives the BGR-swapped image of get_raw_prediction (:381) unchanged
+    FINAL_RESIZE_MODE = 1       # bicubic, align_corners=False (:487-497)
+    CONFIGS = BEIT_CONFIGS
+    NEEDS_READOUT = True
+
+    def net_size(self, W, H, net_w, net_h):
+        return midas_net_size(W, H, net_w, net_h)
+
+    def _pack(self, sd):
+        import torch
+        dev = self.device
+        cfg = self.cfg
+        C = cfg['embed_dim']
+        f16 = lambda t: t.detach().to(dev, torch.float16).contiguous()
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        # re-key the MiDaS checkpoint into the layout the shared packer understands
+        m = {}
+        p = 'pretrained.model.'
+        m['pretrained.patch_embed.proj.weight'] = sd[p + 'patch_embed.proj.weight']
+        m['pretrained.patch_embed.proj.bias'] = sd[p + 'patch_embed.proj.bias']
+        m['pretrained.cls_token'] = sd[p + 'cls_token']
+        m['pretrained.pos_embed'] = torch.zeros(1, 1, C)
+        for i in range(cfg['depth']):
+            b, d = p + f'blocks.{i}.', f'pretrained.blocks.{i}.'
+            for k in ('norm1.weight', 'norm1.bias', 'attn.qkv.weight', 'attn.proj.weight', 'attn.proj.bias', 'norm2.weight', 'norm2.bias',
+                      'mlp.fc1.weight', 'mlp.fc1.bias', 'mlp.fc2.weight', 'mlp.fc2.bias'):
+                m[d + k] = sd[b + k]
+            m[d + 'attn.qkv.bias'] = torch.cat((sd[b + 'attn.q_bias'].float(), torch.zeros(C), sd[b + 'attn.v_bias'].float()))
+            m[d + 'ls1.gamma'] = sd[b + 'gamma_1']
+            m[d + 'ls2.gamma'] = sd[b + 'gamma_2']
+        m['pretrained.norm.weight'] = torch.ones(C)
+        m['pretrained.norm.bias'] = torch.zeros(C)
+        for j in range(4):
+            a = f'pretrained.act_postprocess{j + 1}.'
+            m[f'depth_head.projects.{j}.weight'] = sd[a + '3.weight']
+            m[f'depth_head.projects.{j}.bias'] = sd[a + '3.bias']
+        for j in (0, 1, 3):
+            a = f'pretrained.act_postprocess{j + 1}.4.'
+            m[f'depth_head.resize_layers.{j}.weight'] = sd[a + 'weight']
+            m[f'depth_head.resize_layers.{j}.bias'] = sd[a + 'bias']
+        for k, v in sd.items():
+            if k.startswith('scratch.layer') or k.startswith('scratch.refinenet'):
+                m['depth_head.' + k] = v
+        m['depth_head.scratch.output_conv1.weight'] = sd['scratch.output_conv.0.weight']
+        m['depth_head.scratch.output_conv1.bias'] = sd['scratch.output_conv.0.bias']
+        m['depth_head.scratch.output_conv2.0.weight'] = sd['scratch.output_conv.2.weight']
+        m['depth_head.scratch.output_conv2.0.bias'] = sd['scratch.output_conv.2.bias']
+        m['depth_head.scratch.output_conv2.2.weight'] = sd['scratch.output_conv.4.weight']
+        m['depth_head.scratch.output_conv2.2.bias'] = sd['scratch.output_conv.4.bias']
+        super()._pack(m)
+        self._pos_embed = None  # BEiT uses no absolute position embedding (use_abs_pos_emb=False)
+        self.w['readout'] = [(f16(sd[f'pretrained.act_postprocess{j + 1}.0.project.0.weight']),
+                              f32(sd[f'pretrained.act_postprocess{j + 1}.0.project.0.bias'])) for j in range(4)]
+        self._tables = [f32(sd[p + f'blocks.{i}.attn.relative_position_bias_table']) for i in range(cfg['depth'])]
+        self._bias_cache = {}
+
+    def rel_tables(self, gh, gw):
+        """Table half of _get_rel_pos_bias (dmidas/backbones/beit.py:29-50): per block, the [nrd, heads] table resized
+        (bilinear) to the current window, laid out [heads, nrd] in fp32 and multiplied by log2(e).  Once per resolution.
+        The gather half (:52-62, relative_position_index) happens inside the attention kernel."""
+        import torch
+        import torch.nn.functional as F
+        key = (gh, gw)
+        if key not in self._bias_cache:
+            win = self.cfg['window']
+            old_h = old_w = 2 * win - 1
+            new_h, new_w = 2 * gh - 1, 2 * gw - 1
+            out = []
+            for t in self._tables:
+                sub = t[:old_h * old_w].reshape(1, old_w, old_h, -1).permute(0, 3, 1, 2)
+                new_sub = F.interpolate(sub, size=(int(new_h), int(new_w)), mode="bilinear")
+                new_sub = new_sub.permute(0, 2, 3, 1).reshape(new_h * new_w, -1)
+                table = torch.cat([new_sub, t[old_h * old_w:]])              # [nrd_new, heads]
+                out.append((table.t().contiguous() * 1.4426950408889634).float().contiguous())
+            self._bias_cache = {key: (out, new_h * new_w + 3)}  # keep one resolution resident
+        return self._bias_cache[key]
+
+    def attention(self, i, b, B, N, heads, C, gh, gw):
+        tabs, nrd = self.rel_tables(gh, gw)
+        self.ops.attention_relpos(b['qkv'], B, gh, gw, heads, (C // heads) ** -0.5, tabs[i], nrd, b['att'])
+
+    def emit_feature(self, b, fi, B, N, C):
+        """forward hook on the raw block output + ProjectReadout: GELU(Linear(cat(tokens, cls)))."""
+        rw, rb = self.w['readout'][fi]
+        _lib.check(self.ops.L.dm_concat_readout_f16(b['x'].data_ptr(), B, N, C, b['cat'].data_ptr(), _lib.stream_ptr()), "dm_concat_readout_f16")
+        self.ops.launches += 1
+        self.ops.gemm(b['cat'], 2 * C, rw, 2 * C, B * (N - 1), C, 2 * C, act=_lib.ACT_GELU, bias=rb, C=b['feat'][fi], ldc=C)
 
 
 class ModelHolder:
@@ -448,9 +607,19 @@ class ModelHolder:
                     raise FileNotFoundError(f"{model_path} not found (depthmap_b200 does not download checkpoints)")
                 sd = torch.load(model_path, map_location='cpu')
             model = DepthAnythingV2Engine(sd, f'vit{letter}', torch.device(device))
+        elif model_type in (1, 2):  # dpt_beit_large_512 / dpt_beit_large_384 (MiDaS 3.1)
+            name = {1: 'beitl16_512', 2: 'beitl16_384'}[model_type]
+            if self.weights_provider is not None:
+                sd = self.weights_provider(model_type)
+            else:
+                model_path = "./models/midas/" + {1: 'dpt_beit_large_512.pt', 2: 'dpt_beit_large_384.pt'}[model_type]
+                if not os.path.exists(model_path):
+                    raise FileNotFoundError(f"{model_path} not found (depthmap_b200 does not download checkpoints)")
+                sd = torch.load(model_path, map_location='cpu')
+            model = DptBeitEngine(sd, name, torch.device(device))
         else:
             raise NotImplementedError(f"model_type {model_type} is not implemented in depthmap_b200 yet "
-                                      f"(implemented: 12, 13, 14 = Depth-Anything-V2 S/B/L)")
+                                      f"(implemented: 1, 2 = DPT-BEiT-L 512/384; 12, 13, 14 = Depth-Anything-V2 S/B/L)")
         self.depth_model = model
         self.depth_model_type = model_type
         self.resize_mode = "minimal"
@@ -498,8 +667,8 @@ class ModelHolder:
         """uint8 CUDA [B,H,W,3] -> (float32 CUDA [B,H,W], invert flag).  Batched form of get_raw_prediction."""
         if self.depth_model is None:
             raise RuntimeError("no depth model loaded; call ensure_models first")
-        if self.depth_model_type in (12, 13, 14):
-            pred = self.depth_model.forward_batch(rgb, net_width)  # estimatedepthanything_v2 passes w as input_size (:552)
+        if self.depth_model_type in (1, 2, 12, 13, 14):
+            pred = self.depth_model.forward_batch(rgb, net_width, net_height)
         else:
             raise NotImplementedError(f"model_type {self.depth_model_type}")
         return pred, self.depth_model_type in [0, 7, 8, 9, 10]

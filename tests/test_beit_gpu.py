@@ -1,0 +1,48 @@
+"""GPU: MiDaS 3.1 DPT-BEiT forward on the tensor-core path vs the fp32 oracle restatement (oracle/beit_dpt.py).
+
+The oracle for this family is "parity unpinned" (timm is absent here, see the oracle header); the bar is the same as
+for DA-v2: max |d_gpu - d_ref| / (max - min of the oracle) on the raw prediction."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(cuda_device, name, hw, net, B, tol_max=2e-3, tol_mean=5e-4):
+    import torch
+    from depthmap_b200.depthmap_generation import DptBeitEngine
+    from oracle import beit_dpt, synth_weights
+    from synth import synth_rgb
+    sd = synth_weights.make_beit_dpt_state_dict(name, seed=3)
+    eng = DptBeitEngine(sd, name, cuda_device)
+    imgs = [synth_rgb(hw[0], hw[1], 10 + s) for s in range(B)]
+    got = eng.forward_batch(torch.from_numpy(np.stack(imgs)).to(cuda_device), net[0], net[1]).cpu().numpy()
+    for i, img in enumerate(imgs):
+        want, inv = beit_dpt.get_raw_prediction(img, sd, name, net[0], net[1])
+        rng = float(want.max() - want.min())
+        assert rng > 0.05
+        mx = float(np.abs(got[i] - want).max()) / rng
+        mean = float(np.abs(got[i] - want).mean()) / rng
+        print(name, hw, net, "normalised max err", mx, "mean", mean)
+        assert mx < tol_max and mean < tol_mean, (name, hw, mx, mean)
+
+
+@pytest.mark.parametrize("hw,net", [((64, 96), (64, 64)), ((96, 96), (96, 96)), ((80, 50), (64, 64))])
+def test_beit_tiny_vs_oracle(cuda_device, hw, net):
+    _check(cuda_device, 'beit_tiny', hw, net, 2)
+
+
+def test_beit_large_512_vs_oracle(cuda_device):
+    _check(cuda_device, 'beitl16_512', (512, 512), (512, 512), 1)
+
+
+def test_modelholder_beit(cuda_device):
+    from PIL import Image
+    from depthmap_b200.depthmap_generation import ModelHolder
+    from oracle import synth_weights
+    from synth import synth_rgb
+    # model_type 2 with a structurally identical small state dict is not possible (fixed config), so only the dispatch is checked
+    mh = ModelHolder()
+    assert ModelHolder.get_default_net_size(1) == [512, 512] and ModelHolder.get_default_net_size(2) == [384, 384]
+    with pytest.raises((FileNotFoundError, NotImplementedError)):
+        mh.ensure_models(1, cuda_device, False)

@@ -1,0 +1,62 @@
+"""CPU, world_size 2 (gloo): the image-sharding + single all-gather logic of the multi-GPU path."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from depthmap_b200.dist import shard_range
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 32, 33, 256):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_range(n, r, world)
+                assert 0 <= lo <= hi <= n
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
+            sizes = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_items, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from depthmap_b200.dist import all_gather_batch, shard_range
+    full = torch.arange(n_items * 6, dtype=torch.int32).reshape(n_items, 2, 3)
+    full16 = (torch.arange(n_items * 4, dtype=torch.int32).reshape(n_items, 4) * 997 % 65536).to(torch.int16).view(torch.uint16)
+    lo, hi = shard_range(n_items, rank, world)
+    g = all_gather_batch(full[lo:hi].clone(), n_items)
+    g16 = all_gather_batch(full16[lo:hi].clone(), n_items)
+    ok = torch.equal(g, full) and torch.equal(g16.view(torch.int16), full16.view(torch.int16)) and g16.dtype == torch.uint16
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [8, 5])
+def test_all_gather_batch_world2(n_items):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

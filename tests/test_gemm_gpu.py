@@ -10,7 +10,8 @@ def _lib():
     return L, L.load()
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (128, 32, 64), (1000, 384, 256), (130, 64, 1024), (4100, 3072, 1024)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (128, 32, 64), (1000, 384, 256), (130, 64, 1024), (4100, 3072, 1024),
+                                   (20000, 1024, 4096), (8300, 256, 256), (70, 256, 64)])
 @pytest.mark.parametrize("mode", ["f32", "f16_bias_gelu"])
 def test_gemm_f16(cuda_device, M, N, K, mode):
     import torch
@@ -37,7 +38,7 @@ def test_gemm_f16(cuda_device, M, N, K, mode):
         assert err < 1e-2 * max(1.0, want.abs().max().item()), (M, N, K, err)
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 64), (2, 20, 37, 64, 32), (2, 19, 19, 128, 128), (1, 74, 74, 256, 256)])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 64), (2, 20, 37, 64, 32), (2, 19, 19, 128, 128), (1, 74, 74, 256, 256), (4, 148, 148, 256, 256)])
 def test_conv3x3_f16(cuda_device, B, H, W, Cin, Cout):
     import torch
     L, lib = _lib()

@@ -22,7 +22,7 @@ def test_attention(cuda_device, B, N, H, with_bias):
     qkv = (torch.randn(B * N, 3 * C, generator=g)).half().to(cuda_device)
     scale = 0.125
     bias = None
-    ld = (N + 7) // 8 * 8
+    ld = (N + 127) // 128 * 128
     if with_bias:
         bias = torch.zeros(H, N, ld, dtype=torch.float16, device=cuda_device)
         bias[:, :, :N] = (torch.randn(H, N, N, generator=g) * 2).half().to(cuda_device)
@@ -125,3 +125,27 @@ def test_im2col_s2_matches_conv(cuda_device):
     got = (cols.float() @ wt.float().t()).view(B, Ho, Wo, Co)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=2, padding=1).permute(0, 2, 3, 1)
     assert (got - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("B,gh,gw,H", [(1, 4, 4, 1), (2, 8, 6, 2), (2, 32, 32, 16), (1, 24, 24, 3)])
+def test_attention_relpos_table(cuda_device, B, gh, gw, H):
+    """BEiT relative-position bias generated inside the kernel vs the dense [H,N,N] gather of the reference."""
+    import torch
+    from oracle.beit_dpt import gen_relative_position_index
+    L, lib = _lib()
+    N, C = gh * gw + 1, H * 64
+    nrd = (2 * gh - 1) * (2 * gw - 1) + 3
+    g = torch.Generator(device="cpu").manual_seed(gh * 100 + gw)
+    qkv = torch.randn(B * N, 3 * C, generator=g).half().to(cuda_device)
+    table = (torch.randn(nrd, H, generator=g) * 2).to(cuda_device)
+    idx = gen_relative_position_index((gh, gw)).to(cuda_device)
+    bias = table[idx.view(-1)].view(N, N, H).permute(2, 0, 1)
+    tab_k = (table.t().contiguous() * 1.4426950408889634).float().contiguous()
+    out = torch.empty(B * N, C, dtype=torch.float16, device=cuda_device)
+    L.check(lib.dm_attention_relpos_f16(qkv.data_ptr(), B, gh, gw, H, 0.125, tab_k.data_ptr(), nrd, out.data_ptr(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q * 0.125) @ k.transpose(-1, -2) + bias.unsqueeze(0)
+    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 6e-3, (B, gh, gw, H, err)
