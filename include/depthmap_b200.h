@@ -134,9 +134,11 @@ int dm_conv3x3_f16(const void *act, int B, int H, int W, int Cin, const void *Wt
 int dm_attention_f16(const void *qkv, int B, int N, int H, float scale, const void *bias, int bias_ld, void *out, void *stream);
 /* Same, with the BEiT relative-position bias generated on the fly (dmidas/backbones/beit.py:29-62): rel_table_log2e is
  * fp32 [H, nrd] = the per-head bias table already resized to the gh x gw window, multiplied by log2(e);
- * nrd = (2gh-1)(2gw-1)+3, N = gh*gw+1 tokens (class token first).  No [H,N,N] bias tensor is materialised. */
-int dm_attention_relpos_f16(const void *qkv, int B, int gh, int gw, int H, float scale, const float *rel_table_log2e, int nrd,
-                            void *out, void *stream);
+ * nrd = (2gh-1)(2gw-1)+3, N = gh*gw+1 tokens (class token first); rel_rowmax_log2e is fp32 [H, N] = max over keys of the
+ * bias of each query (same scaling), a setup-time constant that gives the online softmax its row-max upper bound.
+ * No [H,N,N] bias tensor is read by the kernel. */
+int dm_attention_relpos_f16(const void *qkv, int B, int gh, int gw, int H, float scale, const float *rel_table_log2e,
+                            const float *rel_rowmax_log2e, int nrd, void *out, void *stream);
 /* uint8 RGB [B,H,W,3] -> (cv2-style bicubic resize to net_h x net_w) -> (x/255 - mean)/std -> fp16 patch matrix
  * [B*(net_h/patch)*(net_w/patch), kpad], K ordered (c, ky, kx); network channel c reads source channel chan_map[c]. */
 int dm_preprocess_patchify(const uint8_t *rgb, int B, int H, int W, int net_h, int net_w, int patch, const float *mean_host,

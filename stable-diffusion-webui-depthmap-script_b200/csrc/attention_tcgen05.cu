@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_kernel(const __grid_cons
 struct Attn2Params {
     AttnParams a;
     const float *rel_table;   // [H, nrd] * log2(e)   (mode 2)
+    const float *rel_rowmax;  // [H, N]: max_k bias(q, k) * log2(e)   (mode 2) — lets pass 1 skip the bias gather
     int nrd, gh, gw;
 };
 
@@ -417,8 +418,10 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
         // constant entry nrd-3 (mult = 0); the class-token key (k = 0) is patched separately below
         int rp_base = 0, rp_mult = 1;
         float rp_k0 = 0.f;                                   // bias of (q, key 0)
+        float rp_rowmax = 0.f;
         if (BIAS_MODE == 2) {
             const int qq = qi < p.N ? qi : 1;
+            rp_rowmax = __ldg(pp.rel_rowmax + (size_t)h * p.N + qq);
             if (qq == 0) { rp_base = pp.nrd - 3; rp_mult = 0; rp_k0 = s_tab[pp.nrd - 1]; }
             else {
                 const int t = qq - 1, qy = t / pp.gw, qx = t % pp.gw;
@@ -441,7 +444,9 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_S + lane_off + c0, r);
                 tmem_ld_wait();
-                if (BIAS_MODE == 0) {
+                if (BIAS_MODE == 0 || BIAS_MODE == 2) {
+                    // mode 2: the softmax only needs an UPPER BOUND of the row max; max_k(scale*s) + max_k(bias) is one,
+                    // and max_k(bias) per (head, query) is a setup-time constant, so the bias gather is skipped here
                     if (full_tile) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
@@ -483,6 +488,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                 }
             }
             if (BIAS_MODE == 0) mx *= p.scale_log2e;
+            if (BIAS_MODE == 2) mx = fmaf(mx, p.scale_log2e, rp_rowmax);
             // ---- fold in PV of the previous tile, then rescale ----
             if (j > 0) {
                 mbar_wait(&pv_full[g], (j - 1) & 1);
@@ -618,7 +624,8 @@ static int launch_attn2(const CUtensorMap &tm, const Attn2Params &pp, cudaStream
     return DM_OK;
 }
 
-int attention_f16(const __half *qkv, const AttnParams &p, cudaStream_t stream, const float *rel_table = nullptr, int nrd = 0, int gh = 0, int gw = 0) {
+int attention_f16(const __half *qkv, const AttnParams &p, cudaStream_t stream, const float *rel_table = nullptr, const float *rel_rowmax = nullptr,
+                  int nrd = 0, int gh = 0, int gw = 0) {
     if (p.C != p.H * AT_D) { set_error("attention_f16: head_dim must be 64"); return DM_E_UNSUPPORTED; }
     CUtensorMap tm;
     int rc = make_tmap_2d(&tm, qkv, (uint64_t)p.B * p.N, (uint64_t)3 * p.C, (uint64_t)3 * p.C, AT_BQ, AT_D);
@@ -631,7 +638,7 @@ int attention_f16(const __half *qkv, const AttnParams &p, cudaStream_t stream, c
     if (use_v1 < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
     if (!use_v1 || rel_table) {
         Attn2Params pp;
-        pp.a = p; pp.rel_table = rel_table; pp.nrd = nrd; pp.gh = gh; pp.gw = gw;
+        pp.a = p; pp.rel_table = rel_table; pp.rel_rowmax = rel_rowmax; pp.nrd = nrd; pp.gh = gh; pp.gw = gw;
         if (rel_table) {
             if (nrd > 4096 || p.N > 2048 || gh * gw + 1 != p.N) { set_error("attention_f16: relative-position table mode supports nrd <= 4096, N <= 2048, N = gh*gw+1"); return DM_E_UNSUPPORTED; }
             return launch_attn2<2>(tm, pp, stream);
@@ -668,12 +675,13 @@ extern "C" __attribute__((visibility("default"))) int dm_attention_f16(const voi
 }
 
 extern "C" __attribute__((visibility("default"))) int dm_attention_relpos_f16(const void *qkv, int B, int gh, int gw, int H, float scale,
-                                                                           const float *rel_table_log2e, int nrd, void *out, void *stream) {
+                                                                           const float *rel_table_log2e, const float *rel_rowmax_log2e, int nrd,
+                                                                           void *out, void *stream) {
     dm::AttnParams p;
     p.B = B; p.N = gh * gw + 1; p.H = H; p.C = H * 64;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.bias = nullptr; p.bias_ld = 0;
     p.out = (__half *)out;
-    if (!rel_table_log2e) { dm::set_error("dm_attention_relpos_f16: table is NULL"); return DM_E_INVALID; }
-    return dm::attention_f16((const __half *)qkv, p, (cudaStream_t)stream, rel_table_log2e, nrd, gh, gw);
+    if (!rel_table_log2e || !rel_rowmax_log2e) { dm::set_error("dm_attention_relpos_f16: table / rowmax is NULL"); return DM_E_INVALID; }
+    return dm::attention_f16((const __half *)qkv, p, (cudaStream_t)stream, rel_table_log2e, rel_rowmax_log2e, nrd, gh, gw);
 }

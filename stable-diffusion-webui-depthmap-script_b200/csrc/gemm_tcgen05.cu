@@ -232,14 +232,39 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
         }
-        __syncwarp();
+        const bool f16_out = p.epi == EPI_STORE_F16 || p.epi == EPI_PIXSHUF;
+        const int hsel = ((c0 - col_begin) >> 5) & 1;          // fp16 outputs: two 32-column chunks share one 64-column round
+        if (f16_out) {
+            // row `lane` of the staging tile holds 64 halves (128 B); this chunk fills 16-byte slots hsel*4 .. hsel*4+3
+            if (hsel == 0) __syncwarp();
+            uint8_t *srow = reinterpret_cast<uint8_t *>(stage) + lane * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4 *>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        __syncwarp();
+            for (int c = 0; c < 4; ++c) {
+                uint4 u;
+                __half2 *h2 = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(v[8 * c + 2 * k], v[8 * c + 2 * k + 1]);
+                *reinterpret_cast<uint4 *>(srow + (((hsel * 4 + c) ^ (lane & 7)) << 4)) = u;
+            }
+            const bool round_done = hsel == 1 || c0 + 32 >= col_end;
+            if (!round_done) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bcur[j] = bnext[j];
+                continue;
+            }
+            __syncwarp();
+        } else {
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4 *>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            __syncwarp();
+        }
         // pixel-shuffle column mapping is uniform for the chunk
+        const int nr0 = f16_out ? n0 - hsel * 32 : n0;          // first column of this round
+        const int ncols_round = f16_out ? (hsel + 1) * 32 : 32;
         int ps_i = 0, ps_j = 0, ps_co = 0;
-        if (p.epi == EPI_PIXSHUF) { const int ij = n0 / p.ps_cout; ps_co = n0 % p.ps_cout; ps_i = ij / p.ps_s; ps_j = ij % p.ps_s; }
+        if (p.epi == EPI_PIXSHUF) { const int ij = nr0 / p.ps_cout; ps_co = nr0 % p.ps_cout; ps_i = ij / p.ps_s; ps_j = ij % p.ps_s; }
         // ---- transposed domain: 8 lanes cover one row's 128 B; all global loads of the chunk are issued first ----
         long long m_r[8];
         bool ok[8];
@@ -247,7 +272,7 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
         for (int it = 0; it < 8; ++it) {
             const int rr = 4 * it + sub;
             m_r[it] = __shfl_sync(0xffffffffu, m, rr);
-            ok[it] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && col_ok;
+            ok[it] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && (f16_out || col_ok);
         }
         if (p.epi == EPI_RESID_F32) {
             float4 x4[8];
@@ -271,50 +296,54 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
                 if (ok[it]) *reinterpret_cast<float4 *>(p.X + m_r[it] * p.ldx + n0 + cc) = a;
             }
         } else {
-            uint2 r1[8], r2[8];
-            if (p.R) {
+            // fp16 outputs: 8 lanes cover one row's 64 columns (128 B = one full line), 16 B per lane
+            const int ch = lane & 7;
+            const bool lane_ok = ch * 8 < ncols_round && nr0 + ch * 8 < p.N;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) if (ok[it]) r1[it] = __ldg(reinterpret_cast<const uint2 *>(p.R + m_r[it] * p.ldr + n0 + cc));
-            }
-            if (p.R2) {
-#pragma unroll
-                for (int it = 0; it < 8; ++it) if (ok[it]) r2[it] = __ldg(reinterpret_cast<const uint2 *>(p.R2 + m_r[it] * p.ldr2 + n0 + cc));
-            }
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rr = 4 * it + sub;
-                const float4 a = *reinterpret_cast<const float4 *>(stage + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
-                if (!ok[it]) continue;
-                float o0 = a.x, o1 = a.y, o2 = a.z, o3 = a.w;
+            for (int hb = 0; hb < 2; ++hb) {      // two batches of four rows keep the residual prefetch at 32 registers
+                uint4 r1[4], r2[4];
                 if (p.R) {
-                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&r1[it].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&r1[it].y));
-                    o0 += f0.x; o1 += f0.y; o2 += f1.x; o3 += f1.y;
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) { const int it = hb * 4 + i4; if (ok[it] && lane_ok) r1[i4] = __ldg(reinterpret_cast<const uint4 *>(p.R + m_r[it] * p.ldr + nr0 + ch * 8)); }
                 }
                 if (p.R2) {
-                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&r2[it].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&r2[it].y));
-                    o0 += f0.x; o1 += f0.y; o2 += f1.x; o3 += f1.y;
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) { const int it = hb * 4 + i4; if (ok[it] && lane_ok) r2[i4] = __ldg(reinterpret_cast<const uint4 *>(p.R2 + m_r[it] * p.ldr2 + nr0 + ch * 8)); }
                 }
-                __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
-                uint2 u;
-                u.x = *reinterpret_cast<const uint32_t *>(&h0);
-                u.y = *reinterpret_cast<const uint32_t *>(&h1);
-                __half *dst;
-                if (p.epi == EPI_PIXSHUF) {
-                    const int s = p.ps_s;
-                    const long long bb = m_r[it] / ((long long)p.ps_h * p.ps_w);
-                    const int rem = (int)(m_r[it] % ((long long)p.ps_h * p.ps_w));
-                    const int y = rem / p.ps_w, x = rem % p.ps_w;
-                    dst = p.C + (((bb * (p.ps_h * s) + (y * s + ps_i)) * (long long)(p.ps_w * s)) + (x * s + ps_j)) * p.ps_cout + ps_co + cc;
-                } else {
-                    dst = p.C + m_r[it] * p.ldc + n0 + cc;
-                }
-                *reinterpret_cast<uint2 *>(dst) = u;
-                if (p.C2 && p.epi != EPI_PIXSHUF) {
-                    const __half2 z = __float2half2_rn(0.f);
-                    h0 = __hmax2(h0, z); h1 = __hmax2(h1, z);
-                    u.x = *reinterpret_cast<const uint32_t *>(&h0);
-                    u.y = *reinterpret_cast<const uint32_t *>(&h1);
-                    *reinterpret_cast<uint2 *>(p.C2 + m_r[it] * p.ldc + n0 + cc) = u;
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const int it = hb * 4 + i4;
+                    const int rr = 4 * it + sub;
+                    uint4 u = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(stage) + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                    if (!ok[it] || !lane_ok) continue;
+                    if (p.R || p.R2) {
+                        __half2 *h2 = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float2 f = __half22float2(h2[k]);
+                            if (p.R) { const float2 a = __half22float2(reinterpret_cast<const __half2 *>(&r1[i4])[k]); f.x += a.x; f.y += a.y; }
+                            if (p.R2) { const float2 a = __half22float2(reinterpret_cast<const __half2 *>(&r2[i4])[k]); f.x += a.x; f.y += a.y; }
+                            h2[k] = __floats2half2_rn(f.x, f.y);
+                        }
+                    }
+                    __half *dst;
+                    if (p.epi == EPI_PIXSHUF) {
+                        const int s_ = p.ps_s;
+                        const long long bb = m_r[it] / ((long long)p.ps_h * p.ps_w);
+                        const int rem = (int)(m_r[it] % ((long long)p.ps_h * p.ps_w));
+                        const int y = rem / p.ps_w, x = rem % p.ps_w;
+                        dst = p.C + (((bb * (p.ps_h * s_) + (y * s_ + ps_i)) * (long long)(p.ps_w * s_)) + (x * s_ + ps_j)) * p.ps_cout + ps_co + ch * 8;
+                    } else {
+                        dst = p.C + m_r[it] * p.ldc + nr0 + ch * 8;
+                    }
+                    *reinterpret_cast<uint4 *>(dst) = u;
+                    if (p.C2 && p.epi != EPI_PIXSHUF) {
+                        const __half2 z = __float2half2_rn(0.f);
+                        __half2 *h2 = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) h2[k] = __hmax2(h2[k], z);
+                        *reinterpret_cast<uint4 *>(p.C2 + m_r[it] * p.ldc + nr0 + ch * 8) = u;
+                    }
                 }
             }
         }
@@ -574,6 +603,192 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_persist_kerne
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// 2-SM variant (cta_group::2): a cluster of two CTAs (one TPC) computes one 256 x 256 tile.  Each CTA stages only ITS
+// 128 rows of A and ITS 128 of the 256 weight rows (16 KB + 16 KB per k-block instead of 16 + 32), the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) and the hardware feeds both tensor cores from both shared memories.  Per SM that
+// is 64 KB of smem traffic (32 written by TMA, 32 read by the MMA) per 512 tensor cycles = the 128 B/clk port limit,
+// versus 96 KB (1.5x over the port) for the single-CTA 128 x 256 kernel, which measured ~1.05 PFLOP/s for that reason.
+//   barriers: TMA of BOTH CTAs completes on the leader's full[s]; tcgen05.commit multicasts to both CTAs' empty[s] and
+//   tmem_full[a]; epilogue warps of both CTAs arrive (remote mbarrier.arrive) on the leader's tmem_empty[a].
+// ---------------------------------------------------------------------------------------------------------------------
+struct PairCfg {
+    static constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, STAGES = 6;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGING_BYTES = 8 * 4096;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256;
+    static constexpr int TMEM_COLS = 512;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {   // arrives on `bar` of BOTH CTAs of the pair
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive on CTA 0's copy of `bar`
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+template <bool CONV>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                             const __grid_constant__ CUtensorMap tmB, GemmParams p,
+                                                                             int num_m_pairs, int num_tiles) {
+    using Cfg = PairCfg;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;
+    float *staging = reinterpret_cast<float *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    uint64_t *empty = full + Cfg::STAGES;
+    uint64_t *tmem_full = empty + Cfg::STAGES;   // [2]
+    uint64_t *tmem_empty = tmem_full + 2;        // [2]  (the leader's copy is the one that is waited on)
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int num_kb = CONV ? 9 * (p.cCin / Cfg::BK) : p.K / Cfg::BK;
+    const int n_tiles = num_tiles / num_m_pairs;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 16); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                int mp, n_blk;
+                tile_coords(tile, num_m_pairs, n_tiles, num_clusters, mp, n_blk);
+                const int m_blk = mp * 2 + (int)rank;
+                int cb = 0, cy0 = 0, cx0 = 0;
+                if (CONV) {
+                    const int tiles_per_img = p.tiles_x * p.tiles_y;
+                    cb = m_blk / tiles_per_img;
+                    const int t = m_blk % tiles_per_img;
+                    cy0 = (t / p.tiles_x) * p.hbox;
+                    cx0 = (t % p.tiles_x) * p.wbox;
+                }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *sa = smem + stage * Cfg::STAGE_BYTES, *sb = sa + Cfg::A_BYTES;
+                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);   // bytes of both CTAs
+                    if (CONV) {
+                        const int cblks = p.cCin / Cfg::BK;
+                        const int tap = kb / cblks, cblk = kb % cblks;
+                        tma_load_4d_2sm(sa, &tmA, &full[stage], cblk * Cfg::BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb);
+                    } else {
+                        tma_load_2d_2sm(sa, &tmA, &full[stage], kb * Cfg::BK, m_blk * Cfg::BM);
+                    }
+                    tma_load_2d_2sm(sb, &tmB, &full[stage], kb * Cfg::BK, n_blk * Cfg::BN + (int)rank * Cfg::BNH);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(2 * Cfg::BM, Cfg::BN, 0, 0, 0);
+            int stage = 0, phase = 0, it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * Cfg::BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES), sb = sa + Cfg::A_BYTES;
+                    const uint64_t adesc = make_desc_kmajor_sw128(sa), bdesc = make_desc_kmajor_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < Cfg::BK / 16; ++k)
+                        umma_f16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty[stage]);
+                    if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int ehalf = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            const int acc = it & 1;
+            int mp, n_blk;
+            tile_coords(tile, num_m_pairs, n_tiles, num_clusters, mp, n_blk);
+            const int m_blk = mp * 2 + (int)rank;
+            long long m;
+            bool row_ok;
+            if (CONV) {
+                const int tiles_per_img = p.tiles_x * p.tiles_y;
+                const int cb = m_blk / tiles_per_img;
+                const int t = m_blk % tiles_per_img;
+                const int y = (t / p.tiles_x) * p.hbox + row / p.wbox, x = (t % p.tiles_x) * p.wbox + row % p.wbox;
+                row_ok = (cb < p.cB) && (y < p.cH) && (x < p.cW);
+                m = ((long long)cb * p.cH + y) * p.cW + x;
+            } else {
+                m = (long long)m_blk * Cfg::BM + row;
+                row_ok = m < p.M;
+            }
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            epilogue_rows_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
+                                          staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -660,6 +875,39 @@ static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
     return DM_OK;
 }
 
+template <bool CONV>
+static int launch_2sm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int m_pairs = (m_tiles + 1) / 2;
+    const int n_tiles = p.N / PairCfg::BN;
+    const int tiles = m_pairs * n_tiles;
+    int clusters = num_sms() / 2;
+    if (tiles < clusters) clusters = tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(PERSIST_THREADS);
+    cfg.dynamicSmemBytes = PairCfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel<CONV>, tmA, tmB, p, m_pairs, tiles));
+    return DM_OK;
+}
+
+static bool use_2sm(const GemmParams &p, int m_tiles) {
+    static int env = -1;
+    if (env < 0) { const char *e = getenv("DEPTHMAP_B200_2SM"); env = (e && e[0] == '0') ? 0 : 1; }
+    return env && p.epi != EPI_HEAD && p.N % 256 == 0 && (long long)((m_tiles + 1) / 2) * (p.N / 256) >= 37;
+}
+
 static bool use_persist(const GemmParams &p, int m_tiles) {
     static int env = -1;
     if (env < 0) { const char *e = getenv("DEPTHMAP_B200_NO_PERSIST"); env = (e && e[0] == '1') ? 0 : 1; }
@@ -671,13 +919,15 @@ int gemm_f16(const __half *A, int lda, const __half *W, int ldw, GemmParams p, c
     if (p.K % 64 != 0 || p.N % 32 != 0) { set_error("gemm_f16: K must be a multiple of 64 and N of 32 (K=%d N=%d)", p.K, p.N); return DM_E_INVALID; }
     if ((lda % 8) || (ldw % 8)) { set_error("gemm_f16: row pitches must be multiples of 8 elements"); return DM_E_INVALID; }
     const int m_tiles = (p.M + 127) / 128;
-    const bool persist = use_persist(p, m_tiles);
-    const int bn = persist ? 256 : ((p.epi == EPI_HEAD) ? p.N : pick_bn(p.N));
+    const bool pair = use_2sm(p, m_tiles);
+    const bool persist = !pair && use_persist(p, m_tiles);
+    const int bn = pair ? 128 : (persist ? 256 : ((p.epi == EPI_HEAD) ? p.N : pick_bn(p.N)));
     CUtensorMap tmA, tmB;
     int rc = make_tmap_2d(&tmA, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda, 128, 64);
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldw, (uint32_t)bn, 64);
     if (rc) return rc;
+    if (pair) return launch_2sm<false>(tmA, tmB, p, m_tiles, stream);
     if (persist) return launch_persist<false>(tmA, tmB, p, m_tiles, stream);
     switch (bn) {
         case 128: return launch_gemm<128, false>(tmA, tmB, p, m_tiles, stream);
@@ -703,13 +953,15 @@ int conv3x3_f16(const __half *act, int B, int H, int W, int Cin, const __half *W
     p.cB = B; p.cH = H; p.cW = W; p.cCin = Cin;
     p.M = B * H * W; p.K = 9 * Cin;
     const int m_tiles = B * p.tiles_x * p.tiles_y;
-    const bool persist = use_persist(p, m_tiles);
-    const int bn = persist ? 256 : ((p.epi == EPI_HEAD) ? p.N : pick_bn(p.N));
+    const bool pair = use_2sm(p, m_tiles);
+    const bool persist = !pair && use_persist(p, m_tiles);
+    const int bn = pair ? 128 : (persist ? 256 : ((p.epi == EPI_HEAD) ? p.N : pick_bn(p.N)));
     CUtensorMap tmA, tmB;
     int rc = make_tmap_nhwc(&tmA, act, B, H, W, Cin, p.hbox, p.wbox);
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, Wt, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)bn, 64);
     if (rc) return rc;
+    if (pair) return launch_2sm<true>(tmA, tmB, p, m_tiles, stream);
     if (persist) return launch_persist<true>(tmA, tmB, p, m_tiles, stream);
     switch (bn) {
         case 128: return launch_gemm<128, true>(tmA, tmB, p, m_tiles, stream);

@@ -108,9 +108,9 @@ class _Ops:
                                            bias_ld, out.data_ptr(), _lib.stream_ptr()), "dm_attention_f16")
         self.launches += 1
 
-    def attention_relpos(self, qkv, B, gh, gw, H, scale, table, nrd, out):
-        _lib.check(self.L.dm_attention_relpos_f16(qkv.data_ptr(), B, gh, gw, H, float(scale), table.data_ptr(), nrd, out.data_ptr(),
-                                                  _lib.stream_ptr()), "dm_attention_relpos_f16")
+    def attention_relpos(self, qkv, B, gh, gw, H, scale, table, rowmax, nrd, out):
+        _lib.check(self.L.dm_attention_relpos_f16(qkv.data_ptr(), B, gh, gw, H, float(scale), table.data_ptr(), rowmax.data_ptr(), nrd,
+                                                  out.data_ptr(), _lib.stream_ptr()), "dm_attention_relpos_f16")
         self.launches += 1
 
     def layernorm(self, x, rows, C, w, b, out, tokens_per_img=1, drop_first=0, eps=1e-6):
@@ -536,18 +536,22 @@ class DptBeitEngine(DepthAnythingV2Engine):
             old_h = old_w = 2 * win - 1
             new_h, new_w = 2 * gh - 1, 2 * gw - 1
             out = []
+            idx = _gen_relative_position_index(gh, gw).to(self.device)       # [N, N]
             for t in self._tables:
                 sub = t[:old_h * old_w].reshape(1, old_w, old_h, -1).permute(0, 3, 1, 2)
                 new_sub = F.interpolate(sub, size=(int(new_h), int(new_w)), mode="bilinear")
                 new_sub = new_sub.permute(0, 2, 3, 1).reshape(new_h * new_w, -1)
                 table = torch.cat([new_sub, t[old_h * old_w:]])              # [nrd_new, heads]
-                out.append((table.t().contiguous() * 1.4426950408889634).float().contiguous())
+                tab = (table.t().contiguous() * 1.4426950408889634).float().contiguous()   # [heads, nrd]
+                # per (head, query) maximum of the bias over all keys: the kernel's row-max upper bound
+                rowmax = torch.stack([tab[hh][idx].max(dim=1).values for hh in range(tab.shape[0])]).contiguous()
+                out.append((tab, rowmax))
             self._bias_cache = {key: (out, new_h * new_w + 3)}  # keep one resolution resident
         return self._bias_cache[key]
 
     def attention(self, i, b, B, N, heads, C, gh, gw):
         tabs, nrd = self.rel_tables(gh, gw)
-        self.ops.attention_relpos(b['qkv'], B, gh, gw, heads, (C // heads) ** -0.5, tabs[i], nrd, b['att'])
+        self.ops.attention_relpos(b['qkv'], B, gh, gw, heads, (C // heads) ** -0.5, tabs[i][0], tabs[i][1], nrd, b['att'])
 
     def emit_feature(self, b, fi, B, N, C):
         """forward hook on the raw block output + ProjectReadout: GELU(Linear(cat(tokens, cls)))."""

@@ -142,7 +142,9 @@ def test_attention_relpos_table(cuda_device, B, gh, gw, H):
     bias = table[idx.view(-1)].view(N, N, H).permute(2, 0, 1)
     tab_k = (table.t().contiguous() * 1.4426950408889634).float().contiguous()
     out = torch.empty(B * N, C, dtype=torch.float16, device=cuda_device)
-    L.check(lib.dm_attention_relpos_f16(qkv.data_ptr(), B, gh, gw, H, 0.125, tab_k.data_ptr(), nrd, out.data_ptr(), L.stream_ptr()))
+    rowmax = (bias.max(dim=2).values * 1.4426950408889634).float().contiguous()
+    L.check(lib.dm_attention_relpos_f16(qkv.data_ptr(), B, gh, gw, H, 0.125, tab_k.data_ptr(), rowmax.data_ptr(), nrd, out.data_ptr(),
+                                        L.stream_ptr()))
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     s = (q * 0.125) @ k.transpose(-1, -2) + bias.unsqueeze(0)
