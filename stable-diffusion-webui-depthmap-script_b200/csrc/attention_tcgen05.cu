@@ -436,26 +436,17 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
             const bool full_tile = nvalid == AT_BKV;
             mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
-            // ---- pass 1: row max in the log2 domain ----
-            float mx = -INFINITY;
+            // ---- first tile only: a real max pass (m_run starts at -inf).  Later tiles use LAZY rescaling: P is
+            // formed against the running max as it stands, the tile max is tracked on the side, and only if it exceeds
+            // the running max by more than 2^8 is the tile redone with the new max (rare; keeps P inside fp16 range).
+            if (j == 0) {
+                float mx = -INFINITY;
 #pragma unroll 1
-            for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
-                if (c0 >= nvalid) break;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + lane_off + c0, r);
-                tmem_ld_wait();
-                if (BIAS_MODE == 0 || BIAS_MODE == 2) {
-                    // mode 2: the softmax only needs an UPPER BOUND of the row max; max_k(scale*s) + max_k(bias) is one,
-                    // and max_k(bias) per (head, query) is a setup-time constant, so the bias gather is skipped here
-                    if (full_tile) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c0 + i < nvalid) ? __uint_as_float(r[i]) : -INFINITY);
-                    }
-                } else {
-                    float bv[32];
+                for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
+                    if (c0 >= nvalid) break;
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_S + lane_off + c0, r);
+                    tmem_ld_wait();
                     if (BIAS_MODE == 1) {
                         const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
 #pragma unroll
@@ -463,34 +454,28 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                             const uint4 u = __ldg(bp + gq);
                             const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) { const float2 bf = __half22float2(h2[k]); bv[gq * 8 + 2 * k] = bf.x * LOG2E; bv[gq * 8 + 2 * k + 1] = bf.y * LOG2E; }
-                        }
-                    } else {
-                        const uint4 *kp = reinterpret_cast<const uint4 *>(s_koff + kbase + c0);
-#pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            const uint4 u = kp[gq];
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                bv[gq * 8 + 2 * k] = s_tab[rp_base - rp_mult * (int)(w[k] & 0xffffu)];
-                                bv[gq * 8 + 2 * k + 1] = s_tab[rp_base - rp_mult * (int)(w[k] >> 16)];
+                                const float2 bf = __half22float2(h2[k]);
+                                const int i = gq * 8 + 2 * k;
+                                float s0 = fmaf(bf.x, LOG2E, __uint_as_float(r[i]) * p.scale_log2e);
+                                float s1 = fmaf(bf.y, LOG2E, __uint_as_float(r[i + 1]) * p.scale_log2e);
+                                if (!full_tile) { s0 = (c0 + i < nvalid) ? s0 : -INFINITY; s1 = (c0 + i + 1 < nvalid) ? s1 : -INFINITY; }
+                                mx = fmaxf(mx, fmaxf(s0, s1));
                             }
                         }
-                        if (kbase + c0 == 0) bv[0] = rp_k0;
-                    }
+                    } else if (full_tile) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float sv = fmaf(__uint_as_float(r[i]), p.scale_log2e, bv[i]);
-                        if (!full_tile) sv = (c0 + i < nvalid) ? sv : -INFINITY;
-                        mx = fmaxf(mx, sv);
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c0 + i < nvalid) ? __uint_as_float(r[i]) : -INFINITY);
                     }
                 }
-            }
-            if (BIAS_MODE == 0) mx *= p.scale_log2e;
-            if (BIAS_MODE == 2) mx = fmaf(mx, p.scale_log2e, rp_rowmax);
-            // ---- fold in PV of the previous tile, then rescale ----
-            if (j > 0) {
+                if (BIAS_MODE == 0) mx *= p.scale_log2e;
+                if (BIAS_MODE == 2) mx = fmaf(mx, p.scale_log2e, rp_rowmax);   // upper bound: max(scale*s) + max(bias)
+                m_run = mx;
+            } else {
+                // fold in PV of the previous tile (computed against the same m_run: no rescale needed yet)
                 mbar_wait(&pv_full[g], (j - 1) & 1);
                 tc_fence_after();
 #pragma unroll
@@ -502,76 +487,83 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                     for (int i = 0; i < 32; ++i) o[c0 + i] += __uint_as_float(r[i]);
                 }
             }
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = ex2_approx(m_run - m_new);
-            l_run *= alpha;
-#pragma unroll
-            for (int d = 0; d < AT_D; ++d) o[d] *= alpha;
-            m_run = m_new;
-            // ---- pass 2: P = exp2(scale*s [+ bias] - m) as fp16 into the swizzled K-major smem tile ----
-            float lsum = 0.f;
+            // ---- P = exp2(scale*s [+ bias] - m_run) as fp16 into the swizzled K-major smem tile ----
+            float lsum, mx_tile;
+            for (int attempt = 0;; ++attempt) {
+                lsum = 0.f;
+                mx_tile = -INFINITY;
+                const float m_use = m_run;
+                // 16-column sub-chunks, ping-pong TMEM loads: sub-chunk c+1 is in flight while c is exponentiated
+                uint32_t rn[16];
+                tmem_ld_32x16(tmem_S + lane_off, rn);
 #pragma unroll 1
-            for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
-                uint32_t packed[16];
-                if (c0 < nvalid) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_S + lane_off + c0, r);
-                    tmem_ld_wait();
-                    float pv[32];
-                    if (BIAS_MODE == 0) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2e, -m_new));
-                    } else if (BIAS_MODE == 1) {
+                for (int c0 = 0; c0 < AT_BKV; c0 += 16) {
+                    float bv[16];
+                    // bias first: it does not depend on S, so its loads overlap the TMEM round trip
+                    if (BIAS_MODE == 1) {
                         const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
 #pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
+                        for (int gq = 0; gq < 2; ++gq) {
                             const uint4 u = __ldg(bp + gq);
                             const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float2 bf = __half22float2(h2[k]);
-                                const int i = gq * 8 + 2 * k;
-                                pv[i] = ex2_approx(fmaf(bf.x, LOG2E, fmaf(__uint_as_float(r[i]), p.scale_log2e, -m_new)));
-                                pv[i + 1] = ex2_approx(fmaf(bf.y, LOG2E, fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -m_new)));
-                            }
+                            for (int k = 0; k < 4; ++k) { const float2 bf = __half22float2(h2[k]); bv[gq * 8 + 2 * k] = bf.x * LOG2E; bv[gq * 8 + 2 * k + 1] = bf.y * LOG2E; }
                         }
-                    } else {
+                    } else if (BIAS_MODE == 2) {
                         const uint4 *kp = reinterpret_cast<const uint4 *>(s_koff + kbase + c0);
 #pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
+                        for (int gq = 0; gq < 2; ++gq) {
                             const uint4 u = kp[gq];
                             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const int i = gq * 8 + 2 * k;
-                                float b0 = s_tab[rp_base - rp_mult * (int)(w[k] & 0xffffu)];
-                                const float b1 = s_tab[rp_base - rp_mult * (int)(w[k] >> 16)];
-                                if (i == 0 && kbase + c0 == 0) b0 = rp_k0;
-                                pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2e, b0 - m_new));
-                                pv[i + 1] = ex2_approx(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, b1 - m_new));
+                                bv[gq * 8 + 2 * k] = s_tab[rp_base - rp_mult * (int)(w[k] & 0xffffu)];
+                                bv[gq * 8 + 2 * k + 1] = s_tab[rp_base - rp_mult * (int)(w[k] >> 16)];
                             }
                         }
+                        if (kbase + c0 == 0) bv[0] = rp_k0;
                     }
-                    if (!full_tile) {
+                    uint32_t r[16];
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) pv[i] = (c0 + i < nvalid) ? pv[i] : 0.f;
+                    for (int i = 0; i < 16; ++i) r[i] = rn[i];
+                    if (c0 + 16 < AT_BKV) tmem_ld_32x16(tmem_S + lane_off + c0 + 16, rn);
+                    uint32_t packed[8];
+                    if (c0 < nvalid) {
+                        float sv[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            sv[i] = BIAS_MODE == 0 ? __uint_as_float(r[i]) * p.scale_log2e : fmaf(__uint_as_float(r[i]), p.scale_log2e, bv[i]);
+                            if (!full_tile) sv[i] = (c0 + i < nvalid) ? sv[i] : -INFINITY;
+                            mx_tile = fmaxf(mx_tile, sv[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            const __half2 h2 = __floats2half2_rn(ex2_approx(sv[i] - m_use), ex2_approx(sv[i + 1] - m_use));
+                            const float2 f2 = __half22float2(h2);   // sum what the MMA will see
+                            lsum += f2.x + f2.y;
+                            packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) packed[i] = 0u;
                     }
+                    // 16 keys = 32 B = two 16-byte chunks of atom (c0 / 64), chunk index ((c0 % 64) / 8 + t) ^ (row % 8)
+                    uint8_t *atom = sPg + (c0 >> 6) * (AT_BQ * 128) + row * 128;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const __half2 h2 = __floats2half2_rn(pv[i], pv[i + 1]);
-                        const float2 f2 = __half22float2(h2);   // sum what the MMA will see
-                        lsum += f2.x + f2.y;
-                        packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
+                    for (int t = 0; t < 2; ++t) {
+                        const int chunk = (((c0 & 63) >> 3) + t) ^ (row & 7);
+                        *reinterpret_cast<uint4 *>(atom + chunk * 16) = make_uint4(packed[4 * t], packed[4 * t + 1], packed[4 * t + 2], packed[4 * t + 3]);
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) packed[i] = 0u;
                 }
-                uint8_t *atom = sPg + (c0 >> 6) * (AT_BQ * 128) + row * 128;
+                const bool need = mx_tile > m_run + 8.0f;
+                if (!__any_sync(0xffffffffu, need)) break;
+                if (need) {   // raise this row's running max and rescale what has been accumulated so far
+                    const float alpha = ex2_approx(m_run - mx_tile);
+                    l_run *= alpha;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int chunk = (((c0 & 63) >> 3) + t) ^ (row & 7);
-                    *reinterpret_cast<uint4 *>(atom + chunk * 16) = make_uint4(packed[4 * t], packed[4 * t + 1], packed[4 * t + 2], packed[4 * t + 3]);
+                    for (int d = 0; d < AT_D; ++d) o[d] *= alpha;
+                    m_run = mx_tile;
                 }
             }
             l_run += lsum;
