@@ -148,32 +148,47 @@ struct RowSmem {
     __device__ __forceinline__ T *at(uint32_t o) const { return reinterpret_cast<T *>(g_smem + o); }
 };
 
+// nd ** exponent of a source column: read from the fp64 row (DM_DEPTH_ND64) or recomputed from the u16 depth row kept in
+// shared memory (DM_DEPTH_U16; one IEEE division, :81) — the latter saves 8 B/px of shared memory, which is what lets two
+// row-CTAs share an SM at 2048 px.
+struct NdSrc {
+    const double *ndp;
+    const uint16_t *dep;
+    uint32_t mn;
+    double den, expo;
+    int pow_kind;
+    __device__ __forceinline__ double get(int col) const {
+        if (ndp) return ndp[col];
+        const double nd = (double)((uint32_t)dep[col] - mn) / den;
+        return pow_ref(nd, expo, pow_kind);
+    }
+};
+
 // :177-192 vertex x in ORIGINAL order (t = 0 and t = n-1 are the sentinels)
 template <bool SHARP>
-__device__ __forceinline__ double vertex_x(int t, int n, int W, const double *ndp, double div_px, double sep_px) {
+__device__ __forceinline__ double vertex_x(int t, int n, int W, const NdSrc &nds, double div_px, double sep_px) {
     if (t == 0) return -1.0 * (double)W;
     if (t == n - 1) return 2.0 * (double)W;
     const int col = SHARP ? ((t - 1) >> 1) : (t - 1);
-    const double coord_d = ndp[col] * div_px;
+    const double coord_d = nds.get(col) * div_px;
     const double coord_x = (double)col + 0.5 + coord_d + sep_px;
     if (!SHARP) return coord_x;
     return ((t - 1) & 1) ? coord_x + 0.45 : coord_x - 0.45;
 }
 
 template <bool SHARP>
-__device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double sep_px, uint32_t dst_off, double *dbg) {
+__device__ void polylines_eye(const RowSmem &sm, const NdSrc &nds, int W, double div_px, double sep_px, uint32_t dst_off, double *dbg) {
     const int tid = threadIdx.x, T_ = blockDim.x;
     const int n = SHARP ? 2 * W + 2 : W + 2;
     const bool fwd = !(div_px < 0.0);
     double *xs = sm.at<double>(sm.xs), *pm = sm.at<double>(sm.pm);
-    const double *ndp = sm.at<double>(sm.ndp);
     uint16_t *order = sm.at<uint16_t>(sm.order);
-    int *off = sm.at<int>(sm.off), *cur = sm.at<int>(sm.cur);
+    int *off = sm.at<int>(sm.off);
     const uint8_t *src = sm.at<uint8_t>(sm.src);
     uint8_t *dst = sm.at<uint8_t>(dst_off);
 
     // 1. vertex x (kept in smem: every later phase reads it), bucket counters
-    for (int t = tid; t < n; t += T_) { const double x = vertex_x<SHARP>(t, n, W, ndp, div_px, sep_px); xs[t] = x; pm[t] = x; }
+    for (int t = tid; t < n; t += T_) { const double x = vertex_x<SHARP>(t, n, W, nds, div_px, sep_px); xs[t] = x; pm[t] = x; }
     for (int b = tid; b < W + 3; b += T_) off[b] = 0;
     __syncthreads();
     // 2. counting sort by bucket(x): 0 for x<0, 1+floor(x) for 0<=x<W, W+1 for x>=W   (vertices 0..n-2 only, :214)
@@ -186,18 +201,18 @@ __device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double se
     if (fwd) block_scan_inclusive<double>(pm, n, -INFINITY, OpMaxD(), false, sm.at<double>(sm.wtot_d));
     else block_scan_inclusive<double>(pm, n, INFINITY, OpMinD(), true, sm.at<double>(sm.wtot_d));
     block_scan_inclusive<int>(off, W + 2, 0, OpAddI(), false, sm.at<int>(sm.wtot_i));  // inclusive: off[b] = end of bucket b
-    for (int b = tid; b < W + 2; b += T_) cur[b] = b == 0 ? 0 : off[b - 1];
-    __syncthreads();
+    // scatter by filling every bucket from its end backwards: no cursor array, and afterwards off[b] = START of bucket b
+    // (== end of bucket b-1); off[W+2] is set to n-1 so that "end of bucket b" is always off[b+1]
     for (int t = tid; t < n - 1; t += T_) {
         const double x = xs[t];
         const int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
-        order[atomicAdd(&cur[b], 1)] = (uint16_t)t;
+        order[atomicSub(&off[b], 1) - 1] = (uint16_t)t;
     }
-    if (tid == 0) order[n - 1] = (uint16_t)(n - 1);
+    if (tid == 0) { order[n - 1] = (uint16_t)(n - 1); off[W + 2] = n - 1; }
     __syncthreads();
     // 3. order inside buckets by (x, original index)
     for (int b = tid; b < W + 2; b += T_) {
-        const int beg = b == 0 ? 0 : off[b - 1], end = off[b];
+        const int beg = off[b], end = off[b + 1];
         if (end - beg < 2) continue;
         if (b == 0 || b == W + 1) {
             // bucket 0: only its maximum matters (predecessor of pixel 0) -> move it last;
@@ -231,12 +246,12 @@ __device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double se
     if (dbg && tid == 0) {
         dbg[0] = n;
         for (int t = 0; t < n; ++t) { dbg[1 + t] = pm[t]; dbg[1 + n + t] = order[t]; dbg[1 + 2 * n + t] = xs[t]; }
-        for (int b = 0; b < W + 2; ++b) dbg[1 + 3 * n + b] = off[b];
+        for (int b = 0; b < W + 2; ++b) dbg[1 + 3 * n + b] = off[b + 1];
     }
     // 4. rasterise: one output pixel per thread iteration (:228-281)
     for (int col = tid; col < W; col += T_) {
         double c0 = 0.5, c1 = 0.5, c2 = 0.5;
-        int i = off[col] - 1;  // last vertex with x < col  (end of bucket `col` == vertices with x < col)
+        int i = off[col + 1] - 1;  // last vertex with x < col  (start of bucket col+1 == number of vertices with x < col)
         int ti = order[i];
         double xi = xs[ti];
         const double colf = (double)col, colp = (double)(col + 1);
@@ -304,17 +319,16 @@ __device__ void polylines_eye(const RowSmem &sm, int W, double div_px, double se
     __syncthreads();
 }
 
-__device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px, int fill, uint32_t dst_off) {
+__device__ void naive_eye(const RowSmem &sm, const NdSrc &nds, int W, double div_px, double sep_px, int fill, uint32_t dst_off) {
     const int tid = threadIdx.x, T_ = blockDim.x;
     uint8_t *dst = sm.at<uint8_t>(dst_off);
     const uint8_t *src = sm.at<uint8_t>(sm.src);
-    const double *ndp = sm.at<double>(sm.ndp);
     int *winner = sm.at<int>(sm.off);
     const bool take_max = div_px < 0.0;  // ascending sweep: the largest source column writes last (:107)
     for (int c = tid; c < W; c += T_) winner[c] = take_max ? -1 : 0x7fffffff;
     __syncthreads();
     for (int col = tid; col < W; col += T_) {
-        const double v = ndp[col] * div_px + sep_px;
+        const double v = nds.get(col) * div_px + sep_px;
         if (!(v > -4.0e9 && v < 4.0e9)) continue;  // NaN / huge: int() gives INT64_MIN in the reference -> out of range
         const long long cd = (long long)col + (long long)v;  // int(): truncation toward zero
         if (cd >= 0 && cd < W) {
@@ -390,29 +404,30 @@ __device__ void naive_eye(const RowSmem &sm, int W, double div_px, double sep_px
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(512, 1) stereo_row_kernel(StereoArgs a, int pow_kind) {
+template <bool POLY>
+__global__ void __launch_bounds__(256, POLY ? 2 : 4) stereo_row_kernel(StereoArgs a, int pow_kind) {
     const int W = a.W, y = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, T_ = blockDim.x;
-    const bool poly = a.fill == DM_FILL_POLYLINES_SOFT || a.fill == DM_FILL_POLYLINES_SHARP;
+    const bool poly = POLY;
     const int n = a.fill == DM_FILL_POLYLINES_SHARP ? 2 * W + 2 : W + 2;
+    const bool u16 = a.depth_kind == DM_DEPTH_U16;
 
     RowSmem sm;
     uint32_t o = 0;
     auto carve = [&](size_t bytes) { const uint32_t p = o; o += (uint32_t)((bytes + 15) & ~(size_t)15); return p; };
     sm.wtot_d = carve(32 * sizeof(double));
     sm.wtot_i = carve(32 * sizeof(int));
-    sm.ndp = carve(sizeof(double) * W);
+    sm.ndp = carve(u16 ? sizeof(uint16_t) * W : sizeof(double) * W);   // u16 depth row, or the fp64 nd row
     sm.xs = carve(poly ? sizeof(double) * n : 16);
     sm.pm = carve(poly ? sizeof(double) * n : (size_t)3 * W);
-    sm.off = carve(sizeof(int) * (W + 3));
-    sm.cur = carve(sizeof(int) * (W + 3));
+    sm.off = carve(sizeof(int) * (W + 4));
+    sm.cur = carve(a.fill == DM_FILL_NAIVE_INTERPOLATING ? sizeof(int) * (W + 3) : 16);
     sm.aux = carve(a.fill == DM_FILL_NAIVE_INTERPOLATING ? sizeof(int) * (W + 1) : 16);
     sm.order = carve(poly ? sizeof(uint16_t) * n : 16);
     sm.src = carve((size_t)3 * W);
     sm.eye[0] = carve((size_t)3 * W);
     sm.eye[1] = carve((size_t)3 * W);
     uint8_t *s_src = sm.at<uint8_t>(sm.src);
-    double *s_ndp = sm.at<double>(sm.ndp);
 
     // ---- load the row: RGB bytes and nd ** exponent --------------------------------------------------------
     const uint8_t *src_g = a.rgb + ((int64_t)b * a.H + y) * (int64_t)W * 3;
@@ -432,18 +447,20 @@ __global__ void __launch_bounds__(512, 1) stereo_row_kernel(StereoArgs a, int po
         for (int i = h + nvec * 16 + tid; i < nbytes; i += T_) s_src[i] = __ldg(src_g + i);
     }
     bool flat = false;
-    if (a.depth_kind == DM_DEPTH_U16) {
+    NdSrc nds;
+    nds.ndp = nullptr; nds.dep = nullptr; nds.mn = 0; nds.den = 1.0; nds.expo = a.exponent; nds.pow_kind = pow_kind;
+    if (u16) {
         const uint16_t *dep = (const uint16_t *)a.depth + ((int64_t)b * a.H + y) * (int64_t)W;
         const uint32_t mn = a.minmax[2 * b], mx = a.minmax[2 * b + 1];
         flat = (mx == mn);
-        const double den = (double)(mx - mn);
-        for (int c = tid; c < W; c += T_) {
-            const double nd = (double)((uint32_t)__ldg(dep + c) - mn) / den;   // :81, float64 true-divide
-            s_ndp[c] = pow_ref(nd, a.exponent, pow_kind);
-        }
+        uint16_t *s_dep = sm.at<uint16_t>(sm.ndp);
+        for (int c = tid; c < W; c += T_) s_dep[c] = __ldg(dep + c);
+        nds.dep = s_dep; nds.mn = mn; nds.den = (double)(mx - mn);   // :81 (d - min) / (max - min), float64 true-divide
     } else {
         const double *dep = (const double *)a.depth + ((int64_t)b * a.H + y) * (int64_t)W;
+        double *s_ndp = sm.at<double>(sm.ndp);
         for (int c = tid; c < W; c += T_) s_ndp[c] = pow_ref(__ldg(dep + c), a.exponent, pow_kind);
+        nds.ndp = s_ndp;
     }
     __syncthreads();
 
@@ -461,12 +478,13 @@ __global__ void __launch_bounds__(512, 1) stereo_row_kernel(StereoArgs a, int po
             for (int c = tid; c < W; c += T_)
                 for (int k = 0; k < 3; ++k) dst[3 * c + k] = poly ? s_src[k] : (uint8_t)0;
             __syncthreads();
-        } else if (a.fill == DM_FILL_POLYLINES_SHARP) {
-            polylines_eye<true>(sm, W, a.div_px[e], a.sep_px[e], dst_off, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
-        } else if (a.fill == DM_FILL_POLYLINES_SOFT) {
-            polylines_eye<false>(sm, W, a.div_px[e], a.sep_px[e], dst_off, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
+        } else if (POLY) {
+            if (a.fill == DM_FILL_POLYLINES_SHARP)
+                polylines_eye<true>(sm, nds, W, a.div_px[e], a.sep_px[e], dst_off, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
+            else
+                polylines_eye<false>(sm, nds, W, a.div_px[e], a.sep_px[e], dst_off, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
         } else {
-            naive_eye(sm, W, a.div_px[e], a.sep_px[e], a.fill, dst_off);
+            naive_eye(sm, nds, W, a.div_px[e], a.sep_px[e], a.fill, dst_off);
         }
     }
 
@@ -524,12 +542,14 @@ __global__ void minmax_u16_init_kernel(uint32_t *ws, int B) {
     if (i < B) { ws[2 * i] = 0xffffffffu; ws[2 * i + 1] = 0u; }
 }
 
-static size_t stereo_smem_bytes(int W, int fill) {
+static size_t stereo_smem_bytes(int W, int fill, int depth_kind) {
     const bool poly = fill == DM_FILL_POLYLINES_SOFT || fill == DM_FILL_POLYLINES_SHARP;
     const size_t n = fill == DM_FILL_POLYLINES_SHARP ? 2 * (size_t)W + 2 : (size_t)W + 2;
     auto r16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    size_t s = r16(32 * 8) + r16(32 * 4) + r16(8 * (size_t)W) + r16(poly ? 8 * n : 16) + r16(poly ? 8 * n : 3 * (size_t)W) + 2 * r16(4 * ((size_t)W + 3)) +
-               r16(fill == DM_FILL_NAIVE_INTERPOLATING ? 4 * ((size_t)W + 1) : 16) + r16(poly ? 2 * n : 16) + 3 * r16(3 * (size_t)W);
+    const bool interp = fill == DM_FILL_NAIVE_INTERPOLATING;
+    size_t s = r16(32 * 8) + r16(32 * 4) + r16((depth_kind == DM_DEPTH_U16 ? 2 : 8) * (size_t)W) + r16(poly ? 8 * n : 16) +
+               r16(poly ? 8 * n : 3 * (size_t)W) + r16(4 * ((size_t)W + 4)) + r16(interp ? 4 * ((size_t)W + 3) : 16) +
+               r16(interp ? 4 * ((size_t)W + 1) : 16) + r16(poly ? 2 * n : 16) + 3 * r16(3 * (size_t)W);
     return s;
 }
 
@@ -559,14 +579,16 @@ extern "C" __attribute__((visibility("default"))) int dm_stereo(const uint8_t *r
     cudaStream_t stream = (cudaStream_t)stream_;
     uint32_t *ws = (uint32_t *)workspace;
 
-    const size_t smem = stereo_smem_bytes(W, p->fill);
+    const size_t smem = stereo_smem_bytes(W, p->fill, p->depth_kind);
+    const bool poly = p->fill == DM_FILL_POLYLINES_SOFT || p->fill == DM_FILL_POLYLINES_SHARP;
     if (smem > 227 * 1024) {
         set_error("dm_stereo: a %d px row needs %zu B of shared memory (> 227 KB); image too wide for this fill mode", W, smem);
         return DM_E_UNSUPPORTED;
     }
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(stereo_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        DM_CUDA_CHECK(cudaFuncSetAttribute(stereo_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        DM_CUDA_CHECK(cudaFuncSetAttribute(stereo_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         configured = 227 * 1024;
     }
     if (p->depth_kind == DM_DEPTH_U16) {
@@ -589,8 +611,9 @@ extern "C" __attribute__((visibility("default"))) int dm_stereo(const uint8_t *r
     a.out[0] = out0; a.out[1] = out1;
     a.dbg = g_stereo_dbg;
     const int pow_kind = p->exponent == 1.0 ? 0 : (p->exponent == 2.0 ? 1 : 2);
-    const int threads = W <= 256 ? 128 : (W <= 1024 ? 256 : 512);
-    stereo_row_kernel<<<dim3(H, B), threads, smem, stream>>>(a, pow_kind);
+    const int threads = W <= 256 ? 128 : 256;
+    if (poly) stereo_row_kernel<true><<<dim3(H, B), threads, smem, stream>>>(a, pow_kind);
+    else stereo_row_kernel<false><<<dim3(H, B), threads, smem, stream>>>(a, pow_kind);
     DM_LAUNCH_CHECK("stereo_row_kernel");
     return DM_OK;
 }
