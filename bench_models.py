@@ -75,7 +75,7 @@ class Dav2Stereo:
 
     def roofline(self, peaks, kernel_ms):
         achieved = self.fc1_flops / (kernel_ms * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<128> (block-0 MLP fc1: M=B*1370, N=4096, K=1024, GELU epilogue)",
+        return {"bound": "tensor", "kernel": "gemm_tcgen05_2sm_kernel (cta_group::2, 256x256 tile pair; block-0 MLP fc1: M=B*1370, N=4096, K=1024, GELU epilogue)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                 "traffic": None, "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "algorithmic_flops_per_launch": self.fc1_flops,
                 "kernel_ms": kernel_ms}
@@ -160,7 +160,7 @@ class DepthBeit512:
 
     def roofline(self, peaks, kernel_ms):
         achieved = self.fc1_flops / (kernel_ms * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<128> (block-0 MLP fc1: M=B*1025, N=4096, K=1024, GELU epilogue)",
+        return {"bound": "tensor", "kernel": "gemm_tcgen05_2sm_kernel (cta_group::2, 256x256 tile pair; block-0 MLP fc1: M=B*1025, N=4096, K=1024, GELU epilogue)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                 "traffic": None, "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "algorithmic_flops_per_launch": self.fc1_flops,
                 "kernel_ms": kernel_ms}
