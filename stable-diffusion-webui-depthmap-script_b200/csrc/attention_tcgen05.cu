@@ -289,15 +289,27 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_kernel(const __grid_cons
 // MUFU-bound softmax of one tile hides behind the MMAs of the other, and every SM sub-partition hosts two softmax
 // warps whose TMEM / shared-memory latencies overlap.  K_j / V_j are fetched once for both query tiles.
 //   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: softmax group A | warps 6-9: softmax group B
-// TMEM (512 columns): S_A [0,128) S_B [128,256) PV_A [256,320) PV_B [320,384).
-// Bias modes: 0 none (DINOv2) | 1 dense fp16 [H,N,ld] | 2 BEiT relative-position table: the per-head table
+// TMEM (512 columns): S_A [0,128) S_B [128,256) PV_A [256,336) PV_B [352,432).
+//
+// What keeps the softmax loop short (it is the critical resource: ~4 issue slots + 1 MUFU per score):
+//   * the PV MMA runs with N = 80: 64 value dims + a 16-wide block of ONES (2 KB of fp16 1.0 in smem, reached through
+//     the MN-major descriptor's leading-dimension offset), so column 64 of PV is the row sum of P exactly as the tensor
+//     core saw it — no unpack-and-add of the rounded probabilities in the loop;
+//   * score = s * scale + (bias - m) is one FADD2 + one FFMA2 per PAIR of columns (fp32x2), the tile max is FMNMX3;
+//   * key tiles are as wide as they need to be: S and PV of the last tile use N / K = ceil16(valid keys), not 128;
+//   * lazy running max (rescale only when the tile max exceeds the running max by 2^8).
+// Bias modes: 0 none (DINOv2) | 1 dense fp16 [H,N,ld] | 2 BEiT relative-position table, generic grid: the per-head table
 // [nrd] (pre-multiplied by log2 e) and the per-key offset ky*(2gw-1)+kx live in shared memory and the bias of (q, k) is
-// table[base_q - koff_k] — no [H,N,N] tensor is ever read (the reference materialises it per block per forward).
+// table[base_q - koff_k] — no [H,N,N] tensor is ever read (the reference materialises it per block per forward)
+// | 3 the same table for grids with gw % 16 == 0 (BEiT-512: 32x32): the tiling is shifted by the class token, i.e. query
+// and key tiles start at token 1, so every 16-key chunk lies inside one grid row and its 16 biases are the CONTIGUOUS
+// table entries base_q - koff(chunk) - i: one LDS with an immediate offset per score, no per-key index arithmetic and no
+// masks.  The class-token KEY is a 16-wide tail tile; the class-token QUERY row is done by attention_cls_row_kernel.
 // =====================================================================================================================
 struct Attn2Params {
     AttnParams a;
-    const float *rel_table;   // [H, nrd] * log2(e)   (mode 2)
-    const float *rel_rowmax;  // [H, N]: max_k bias(q, k) * log2(e)   (mode 2) — lets pass 1 skip the bias gather
+    const float *rel_table;   // [H, nrd] * log2(e)   (modes 2, 3)
+    const float *rel_rowmax;  // [H, N]: max_k bias(q, k) * log2(e)   (modes 2, 3) — lets the first-tile max pass skip the bias gather
     int nrd, gh, gw;
 };
 
@@ -305,28 +317,66 @@ constexpr int A2_THREADS = 64 + 256;
 constexpr int A2_Q_BYTES = 2 * AT_Q_BYTES;                 // 32 KB
 constexpr int A2_KV_BYTES = AT_STAGES * 2 * AT_KV_BYTES;   // 64 KB
 constexpr int A2_P_BYTES = 2 * AT_P_BYTES;                 // 64 KB
-constexpr int A2_TAB_BYTES = 16384 + 4096;                 // fp32 table (<= 4096 entries) + u16 key offsets (<= 2048 keys)
-constexpr int A2_SMEM_BASE = A2_Q_BYTES + A2_KV_BYTES + A2_P_BYTES + 256;
+constexpr int A2_ONES_BYTES = 2048;                        // 16 key rows x 128 B of fp16 1.0
+constexpr int A2_TAB_BYTES = 16384 + 4096;                 // fp32 table (<= 4096 entries) + key offsets
+constexpr int A2_SMEM_BASE = A2_Q_BYTES + A2_KV_BYTES + A2_P_BYTES + A2_ONES_BYTES + 256;
+constexpr int A2_PV_N = 80, A2_PV_STRIDE = 96;
+
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
+
+struct TagTrue { static constexpr bool value = true; };
+struct TagFalse { static constexpr bool value = false; };
 
 template <int BIAS_MODE>
 __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, Attn2Params pp) {
     const AttnParams &p = pp.a;
+    constexpr bool ALIGNED = BIAS_MODE == 3;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *sQ = smem_raw;                                  // tile A at +0, tile B at +16 KB
     uint8_t *sKV = sQ + A2_Q_BYTES;
     uint8_t *sP = sKV + A2_KV_BYTES;                         // P_A at +0, P_B at +32 KB
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + A2_P_BYTES);
+    uint8_t *sOnes = sP + A2_P_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sOnes + A2_ONES_BYTES);
     uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3;
     uint64_t *s_full = bars + 5, *p_full = bars + 7, *pv_full = bars + 9;   // [2] each, index = group
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 11);
     float *s_tab = reinterpret_cast<float *>(smem_raw + A2_SMEM_BASE);
-    uint16_t *s_koff = reinterpret_cast<uint16_t *>(smem_raw + A2_SMEM_BASE + 16384);
+    uint16_t *s_koff = reinterpret_cast<uint16_t *>(smem_raw + A2_SMEM_BASE + 16384);   // mode 2: per key; mode 3: per 16-key chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int q0 = qp * 2 * AT_BQ;
-    const bool b_active = q0 + AT_BQ < p.N;                   // second tile may be entirely out of range
-    const int num_kv = (p.N + AT_BKV - 1) / AT_BKV;
+    // token geometry.  ALIGNED: tiles cover tokens 1 .. N-1 (the patch grid); key 0 (class token) is the tail tile.
+    const int tok0 = ALIGNED ? 1 : 0;
+    const int ntok = p.N - tok0;
+    const int num_main = (ntok + AT_BKV - 1) / AT_BKV;
+    const int num_kv = num_main + (ALIGNED ? 1 : 0);
+    const int q0 = qp * 2 * AT_BQ;                            // first query of the CTA, relative to tok0
+    const bool b_active = q0 + AT_BQ < ntok;                  // second tile may be entirely out of range
     const int row_base = b * p.N;
 
     if (warp == 0 && lane == 0) {
@@ -337,14 +387,23 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
-    if (BIAS_MODE == 2) {
+    for (int i = threadIdx.x; i < A2_ONES_BYTES / 4; i += A2_THREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3c003c00u;
+    if (BIAS_MODE >= 2) {
         const float *tab = pp.rel_table + (size_t)h * pp.nrd;
         for (int i = threadIdx.x; i < pp.nrd; i += A2_THREADS) s_tab[i] = __ldg(tab + i);
-        for (int k = threadIdx.x; k < num_kv * AT_BKV; k += A2_THREADS) {
-            const int t = k - 1;
-            s_koff[k] = (k >= 1 && k < p.N) ? (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw)) : (uint16_t)0;
+        if (ALIGNED) {
+            for (int c = threadIdx.x; c < num_main * (AT_BKV / 16); c += A2_THREADS) {
+                const int t = c * 16;
+                s_koff[c] = (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw));
+            }
+        } else {
+            for (int k = threadIdx.x; k < num_kv * AT_BKV; k += A2_THREADS) {
+                const int t = k - 1;
+                s_koff[k] = (k >= 1 && k < p.N) ? (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw)) : (uint16_t)0;
+            }
         }
     }
+    fence_proxy_async();          // the ones block is read by the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -353,25 +412,29 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, b_active ? 2 * AT_Q_BYTES : AT_Q_BYTES);
-            tma_load_2d(sQ, &tmQKV, q_full, h * AT_D, row_base + q0);
-            if (b_active) tma_load_2d(sQ + AT_Q_BYTES, &tmQKV, q_full, h * AT_D, row_base + q0 + AT_BQ);
+            tma_load_2d(sQ, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0);
+            if (b_active) tma_load_2d(sQ + AT_Q_BYTES, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0 + AT_BQ);
             for (int j = 0; j < num_kv; ++j) {
                 const int s = j & 1;
+                const int key0 = (ALIGNED && j == num_main) ? 0 : tok0 + j * AT_BKV;
                 mbar_wait_backoff(&kv_empty[s], ((j >> 1) & 1) ^ 1);
                 uint8_t *sk = sKV + s * 2 * AT_KV_BYTES, *sv = sk + AT_KV_BYTES;
                 mbar_arrive_expect_tx(&kv_full[s], 2 * AT_KV_BYTES);
-                tma_load_2d(sk, &tmQKV, &kv_full[s], p.C + h * AT_D, row_base + j * AT_BKV);
-                tma_load_2d(sv, &tmQKV, &kv_full[s], 2 * p.C + h * AT_D, row_base + j * AT_BKV);
+                tma_load_2d(sk, &tmQKV, &kv_full[s], p.C + h * AT_D, row_base + key0);
+                tma_load_2d(sv, &tmQKV, &kv_full[s], 2 * p.C + h * AT_D, row_base + key0);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc_qk = make_idesc_f16(AT_BQ, AT_BKV, 0, 0, 0);
-            constexpr uint32_t idesc_pv = make_idesc_f16(AT_BQ, AT_D, 0, 0, 1);  // B (= V) is MN-major
+            constexpr uint32_t idesc_pv = make_idesc_f16(AT_BQ, A2_PV_N, 0, 0, 1);  // B (= V | ones) is MN-major
+            const uint32_t ones_addr = smem_u32(sOnes);
             mbar_wait_backoff(q_full, 0);
             const int ngroups = b_active ? 2 : 1;
             for (int j = 0; j < num_kv; ++j) {
                 const int s = j & 1;
+                const int nvalid = (ALIGNED && j == num_main) ? 1 : min(AT_BKV, ntok - j * AT_BKV);
+                const int ncols = (nvalid + 15) & ~15;
+                const uint32_t idesc_qk = make_idesc_f16(AT_BQ, ncols, 0, 0, 0);
                 mbar_wait_backoff(&kv_full[s], (j >> 1) & 1);
                 tc_fence_after();
                 const uint32_t sk = smem_u32(sKV + s * 2 * AT_KV_BYTES), sv = sk + AT_KV_BYTES;
@@ -383,15 +446,15 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                         umma_f16(tmem_base + g * 128, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_qk, k != 0);
                     umma_commit(&s_full[g]);
                 }
-                for (int g = 0; g < ngroups; ++g) {   // PV_g = P_g V_j once group g has written P_g
+                for (int g = 0; g < ngroups; ++g) {   // PV_g = P_g [V_j | 1] once group g has written P_g
                     mbar_wait_backoff(&p_full[g], j & 1);
                     tc_fence_after();
                     const uint32_t sp = smem_u32(sP + g * AT_P_BYTES);
-#pragma unroll
-                    for (int k = 0; k < AT_BKV / 16; ++k) {
+                    for (int k = 0; k < (ncols >> 4); ++k) {
                         const uint64_t pdesc = make_desc_kmajor_sw128(sp + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32);
-                        const uint64_t vdesc = make_desc_mnmajor_sw128(sv + k * 16 * 128, 16 * 128);
-                        umma_f16(tmem_base + 256 + g * 64, pdesc, vdesc, idesc_pv, k != 0);
+                        const uint32_t vaddr = sv + k * 16 * 128;
+                        const uint64_t vdesc = make_desc_mnmajor_sw128(vaddr, ones_addr - vaddr);   // second 64-wide MN block = ones
+                        umma_f16(tmem_base + 256 + g * A2_PV_STRIDE, pdesc, vdesc, idesc_pv, k != 0);
                     }
                     umma_commit(&pv_full[g]);
                 }
@@ -405,22 +468,24 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const uint32_t tmem_S = tmem_base + g * 128, tmem_PV = tmem_base + 256 + g * 64;
+        const uint32_t tmem_S = tmem_base + g * 128 + lane_off, tmem_PV = tmem_base + 256 + g * A2_PV_STRIDE + lane_off;
         uint8_t *sPg = sP + g * AT_P_BYTES;
-        const int qi = q0 + g * AT_BQ + row;           // query index inside the image
-        float m_run = -INFINITY, l_run = 0.f;
-        float o[AT_D];
+        const int tq = q0 + g * AT_BQ + row;           // query, relative to tok0
+        const bool q_ok = tq < ntok;
+        const int qi = tok0 + tq;                      // query index inside the image
+        float m_run = -INFINITY;
+        float o[AT_D + 1];                             // o[64] = running row sum
 #pragma unroll
-        for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
+        for (int d = 0; d <= AT_D; ++d) o[d] = 0.f;
         constexpr float LOG2E = 1.4426950408889634f;
-        const __half *brow = BIAS_MODE == 1 ? p.bias + ((size_t)h * p.N + (qi < p.N ? qi : 0)) * p.bias_ld : nullptr;
-        // relative-position table addressing: idx(q, k) = base_q - mult * koff_k; the class-token query uses the
-        // constant entry nrd-3 (mult = 0); the class-token key (k = 0) is patched separately below
+        const __half *brow = BIAS_MODE == 1 ? p.bias + ((size_t)h * p.N + (q_ok ? qi : 0)) * p.bias_ld : nullptr;
+        // relative-position table addressing: idx(q, k) = base_q - mult * koff_k; generic mode: the class-token query uses
+        // the constant entry nrd-3 (mult = 0); the class-token key (k = 0) is patched separately below
         int rp_base = 0, rp_mult = 1;
         float rp_k0 = 0.f;                                   // bias of (q, key 0)
         float rp_rowmax = 0.f;
-        if (BIAS_MODE == 2) {
-            const int qq = qi < p.N ? qi : 1;
+        if (BIAS_MODE >= 2) {
+            const int qq = q_ok ? qi : 1;
             rp_rowmax = __ldg(pp.rel_rowmax + (size_t)h * p.N + qq);
             if (qq == 0) { rp_base = pp.nrd - 3; rp_mult = 0; rp_k0 = s_tab[pp.nrd - 1]; }
             else {
@@ -429,11 +494,25 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                 rp_k0 = s_tab[pp.nrd - 2];
             }
         }
+        const uint64_t scale2 = pack2(p.scale_log2e, p.scale_log2e);
+
+        // fold the finished PV accumulator (64 dims + the row-sum column) of the previous tile into the registers
+        auto fold_pv = [&]() {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(tmem_PV, r0);
+            tmem_ld_32x32(tmem_PV + 32, r1);
+            const uint32_t rs = tmem_ld_32x1(tmem_PV + 64);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { o[i] += __uint_as_float(r0[i]); o[32 + i] += __uint_as_float(r1[i]); }
+            o[AT_D] += __uint_as_float(rs);
+        };
 
         for (int j = 0; j < num_kv; ++j) {
-            const int kbase = j * AT_BKV;
-            const int nvalid = min(AT_BKV, p.N - kbase);
-            const bool full_tile = nvalid == AT_BKV;
+            const bool tail = ALIGNED && j == num_main;
+            const int kbase = tail ? 0 : tok0 + j * AT_BKV;                 // first key (token index) of the tile
+            const int nvalid = tail ? 1 : min(AT_BKV, ntok - j * AT_BKV);
+            const int ncols = (nvalid + 15) & ~15;
             mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
             // ---- first tile only: a real max pass (m_run starts at -inf).  Later tiles use LAZY rescaling: P is
@@ -444,8 +523,9 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
 #pragma unroll 1
                 for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
                     if (c0 >= nvalid) break;
+                    const bool full32 = c0 + 32 <= nvalid;
                     uint32_t r[32];
-                    tmem_ld_32x32(tmem_S + lane_off + c0, r);
+                    tmem_ld_32x32(tmem_S + c0, r);
                     tmem_ld_wait();
                     if (BIAS_MODE == 1) {
                         const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
@@ -459,47 +539,37 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                                 const int i = gq * 8 + 2 * k;
                                 float s0 = fmaf(bf.x, LOG2E, __uint_as_float(r[i]) * p.scale_log2e);
                                 float s1 = fmaf(bf.y, LOG2E, __uint_as_float(r[i + 1]) * p.scale_log2e);
-                                if (!full_tile) { s0 = (c0 + i < nvalid) ? s0 : -INFINITY; s1 = (c0 + i + 1 < nvalid) ? s1 : -INFINITY; }
+                                if (!full32) { s0 = (c0 + i < nvalid) ? s0 : -INFINITY; s1 = (c0 + i + 1 < nvalid) ? s1 : -INFINITY; }
                                 mx = fmaxf(mx, fmaxf(s0, s1));
                             }
                         }
-                    } else if (full_tile) {
+                    } else if (full32) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c0 + i < nvalid) ? __uint_as_float(r[i]) : -INFINITY);
                     }
                 }
                 if (BIAS_MODE == 0) mx *= p.scale_log2e;
-                if (BIAS_MODE == 2) mx = fmaf(mx, p.scale_log2e, rp_rowmax);   // upper bound: max(scale*s) + max(bias)
+                if (BIAS_MODE >= 2) mx = fmaf(mx, p.scale_log2e, rp_rowmax);   // upper bound: max(scale*s) + max(bias)
                 m_run = mx;
             } else {
                 // fold in PV of the previous tile (computed against the same m_run: no rescale needed yet)
                 mbar_wait(&pv_full[g], (j - 1) & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < AT_D; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_PV + lane_off + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o[c0 + i] += __uint_as_float(r[i]);
-                }
+                fold_pv();
             }
             // ---- P = exp2(scale*s [+ bias] - m_run) as fp16 into the swizzled K-major smem tile ----
-            float lsum, mx_tile;
+            float mx_rel;                          // max over the tile of (score - m_run)
             for (int attempt = 0;; ++attempt) {
-                lsum = 0.f;
-                mx_tile = -INFINITY;
-                const float m_use = m_run;
-                // 16-column sub-chunks, ping-pong TMEM loads: sub-chunk c+1 is in flight while c is exponentiated
-                uint32_t rn[16];
-                tmem_ld_32x16(tmem_S + lane_off, rn);
-#pragma unroll 1
-                for (int c0 = 0; c0 < AT_BKV; c0 += 16) {
+                mx_rel = -INFINITY;
+                const float neg_m = -m_run;
+                const uint64_t negm2 = pack2(neg_m, neg_m);
+                // one 16-column chunk: scores -> probabilities -> two 16-byte stores into the P tile
+                auto chunk = [&](const uint32_t (&r)[16], int c0, auto partial_tag) {
+                    constexpr bool PARTIAL = decltype(partial_tag)::value;   // only the last chunk of a ragged tile masks
                     float bv[16];
-                    // bias first: it does not depend on S, so its loads overlap the TMEM round trip
                     if (BIAS_MODE == 1) {
                         const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
 #pragma unroll
@@ -522,51 +592,59 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                             }
                         }
                         if (kbase + c0 == 0) bv[0] = rp_k0;
+                    } else if (BIAS_MODE == 3) {
+                        if (tail) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) bv[i] = rp_k0;
+                        } else {
+                            const float *tp = s_tab + (rp_base - (int)s_koff[(j * AT_BKV + c0) >> 4]);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) bv[i] = *(tp - i);
+                        }
                     }
-                    uint32_t r[16];
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = rn[i];
-                    if (c0 + 16 < AT_BKV) tmem_ld_32x16(tmem_S + lane_off + c0 + 16, rn);
                     uint32_t packed[8];
-                    if (c0 < nvalid) {
-                        float sv[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            sv[i] = BIAS_MODE == 0 ? __uint_as_float(r[i]) * p.scale_log2e : fmaf(__uint_as_float(r[i]), p.scale_log2e, bv[i]);
-                            if (!full_tile) sv[i] = (c0 + i < nvalid) ? sv[i] : -INFINITY;
-                            mx_tile = fmaxf(mx_tile, sv[i]);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
-                            const __half2 h2 = __floats2half2_rn(ex2_approx(sv[i] - m_use), ex2_approx(sv[i + 1] - m_use));
-                            const float2 f2 = __half22float2(h2);   // sum what the MMA will see
-                            lsum += f2.x + f2.y;
-                            packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) packed[i] = 0u;
+                    for (int i = 0; i < 16; i += 2) {
+                        const uint64_t b2 = BIAS_MODE == 0 ? negm2 : add2(pack2(bv[i], bv[i + 1]), negm2);
+                        float t0, t1;
+                        unpack2(fma2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, b2), t0, t1);
+                        if (PARTIAL) { t0 = (c0 + i < nvalid) ? t0 : -INFINITY; t1 = (c0 + i + 1 < nvalid) ? t1 : -INFINITY; }
+                        mx_rel = max3(mx_rel, t0, t1);
+                        const __half2 h2 = __floats2half2_rn(ex2_approx(t0), ex2_approx(t1));
+                        packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
                     }
                     // 16 keys = 32 B = two 16-byte chunks of atom (c0 / 64), chunk index ((c0 % 64) / 8 + t) ^ (row % 8)
                     uint8_t *atom = sPg + (c0 >> 6) * (AT_BQ * 128) + row * 128;
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
-                        const int chunk = (((c0 & 63) >> 3) + t) ^ (row & 7);
-                        *reinterpret_cast<uint4 *>(atom + chunk * 16) = make_uint4(packed[4 * t], packed[4 * t + 1], packed[4 * t + 2], packed[4 * t + 3]);
+                        const int ch = (((c0 & 63) >> 3) + t) ^ (row & 7);
+                        *reinterpret_cast<uint4 *>(atom + ch * 16) = make_uint4(packed[4 * t], packed[4 * t + 1], packed[4 * t + 2], packed[4 * t + 3]);
+                    }
+                };
+                // two register buffers, alternating: the TMEM load of chunk c+1 is in flight while chunk c is exponentiated
+                uint32_t ra[16], rb[16];
+                tmem_ld_32x16(tmem_S, ra);
+#pragma unroll 1
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    tmem_ld_wait();
+                    const bool has_b = c0 + 16 < ncols;
+                    if (has_b) tmem_ld_32x16(tmem_S + c0 + 16, rb);
+                    if (c0 + 16 > nvalid) chunk(ra, c0, TagTrue()); else chunk(ra, c0, TagFalse());
+                    if (has_b) {
+                        tmem_ld_wait();
+                        if (c0 + 32 < ncols) tmem_ld_32x16(tmem_S + c0 + 32, ra);
+                        if (c0 + 32 > nvalid) chunk(rb, c0 + 16, TagTrue()); else chunk(rb, c0 + 16, TagFalse());
                     }
                 }
-                const bool need = mx_tile > m_run + 8.0f;
+                const bool need = mx_rel > 8.0f;
                 if (!__any_sync(0xffffffffu, need)) break;
                 if (need) {   // raise this row's running max and rescale what has been accumulated so far
-                    const float alpha = ex2_approx(m_run - mx_tile);
-                    l_run *= alpha;
+                    const float alpha = ex2_approx(-mx_rel);
 #pragma unroll
-                    for (int d = 0; d < AT_D; ++d) o[d] *= alpha;
-                    m_run = mx_tile;
+                    for (int d = 0; d <= AT_D; ++d) o[d] *= alpha;
+                    m_run += mx_rel;
                 }
             }
-            l_run += lsum;
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(&p_full[g]);
@@ -574,16 +652,9 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
         // ---- last PV, normalise, store ----
         mbar_wait(&pv_full[g], (num_kv - 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < AT_D; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_PV + lane_off + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[c0 + i] += __uint_as_float(r[i]);
-        }
-        if (qi < p.N) {
-            const float inv = 1.0f / l_run;
+        fold_pv();
+        if (q_ok) {
+            const float inv = 1.0f / o[AT_D];
             __half *dst = p.out + (size_t)(row_base + qi) * p.C + h * AT_D;
 #pragma unroll
             for (int d = 0; d < AT_D; d += 8) {
@@ -602,17 +673,83 @@ done:
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// Class-token query row of the aligned BEiT mode: one CTA per (head, image), plain SIMT (N scores of one row).
+// Its bias is the constant class->patch entry (nrd-3) for every key and the class->class entry (nrd-1) for key 0
+// (dmidas/backbones/beit.py:44-62 assembles exactly these three extra entries).  P is rounded to fp16 before the
+// weighted sum, like the tensor-core path.
+__global__ void __launch_bounds__(256) attention_cls_row_kernel(const __half *__restrict__ qkv, Attn2Params pp) {
+    const AttnParams &p = pp.a;
+    extern __shared__ float cls_smem[];
+    float *sc = cls_smem;                 // [N] scores, then probabilities
+    float *red = sc + ((p.N + 31) & ~31); // [256] reduction scratch / partial outputs
+    float *sq = red + 256;                // [64] query
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const size_t ld = (size_t)3 * p.C;
+    const __half *base = qkv + (size_t)b * p.N * ld + h * AT_D;
+    if (tid < AT_D) sq[tid] = __half2float(base[tid]);
+    __syncthreads();
+    const float *tab = pp.rel_table + (size_t)h * pp.nrd;
+    const float b_tok = __ldg(tab + pp.nrd - 3), b_cls = __ldg(tab + pp.nrd - 1);
+    float mx = -INFINITY;
+    for (int k = tid; k < p.N; k += 256) {
+        const uint4 *kr = reinterpret_cast<const uint4 *>(base + (size_t)k * ld + p.C);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = __ldg(kr + c);
+            const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h2[e]); acc = fmaf(sq[c * 8 + 2 * e], f.x, acc); acc = fmaf(sq[c * 8 + 2 * e + 1], f.y, acc); }
+        }
+        const float s = fmaf(acc, p.scale_log2e, k == 0 ? b_cls : b_tok);
+        sc[k] = s;
+        mx = fmaxf(mx, s);
+    }
+    red[tid] = mx;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]); __syncthreads(); }
+    mx = red[0];
+    __syncthreads();
+    float sum = 0.f;
+    for (int k = tid; k < p.N; k += 256) {
+        const float pr = __half2float(__float2half_rn(ex2_approx(sc[k] - mx)));
+        sc[k] = pr;
+        sum += pr;
+    }
+    red[tid] = sum;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
+    sum = red[0];
+    __syncthreads();
+    // weighted sum: thread = (key phase kg of 4, dim d)
+    const int d = tid & 63, kg = tid >> 6;
+    float acc = 0.f;
+    for (int k = kg; k < p.N; k += 4) acc = fmaf(sc[k], __half2float(base[(size_t)k * ld + 2 * p.C + d]), acc);
+    red[tid] = acc;
+    __syncthreads();
+    if (tid < AT_D) {
+        const float v = (red[tid] + red[tid + 64] + red[tid + 128] + red[tid + 192]) / sum;
+        p.out[(size_t)b * p.N * p.C + h * AT_D + tid] = __float2half_rn(v);
+    }
+}
+
 template <int MODE>
-static int launch_attn2(const CUtensorMap &tm, const Attn2Params &pp, cudaStream_t stream) {
-    const int smem = A2_SMEM_BASE + (MODE == 2 ? A2_TAB_BYTES : 0);
+static int launch_attn2(const CUtensorMap &tm, const Attn2Params &pp, cudaStream_t stream, const __half *qkv) {
+    const int smem = A2_SMEM_BASE + (MODE >= 2 ? A2_TAB_BYTES : 0);
     static bool configured = false;
     if (!configured) {
         DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid((pp.a.N + 2 * AT_BQ - 1) / (2 * AT_BQ), pp.a.H, pp.a.B);
+    const int ntok = pp.a.N - (MODE == 3 ? 1 : 0);
+    dim3 grid((ntok + 2 * AT_BQ - 1) / (2 * AT_BQ), pp.a.H, pp.a.B);
     attention_fwd2_kernel<MODE><<<grid, A2_THREADS, smem, stream>>>(tm, pp);
     DM_LAUNCH_CHECK("attention_fwd2_kernel");
+    if (MODE == 3) {
+        const int cls_smem = (((pp.a.N + 31) & ~31) + 256 + 64) * (int)sizeof(float);
+        attention_cls_row_kernel<<<dim3(pp.a.H, pp.a.B), 256, cls_smem, stream>>>(qkv, pp);
+        DM_LAUNCH_CHECK("attention_cls_row_kernel");
+    }
     return DM_OK;
 }
 
@@ -633,9 +770,11 @@ int attention_f16(const __half *qkv, const AttnParams &p, cudaStream_t stream, c
         pp.a = p; pp.rel_table = rel_table; pp.rel_rowmax = rel_rowmax; pp.nrd = nrd; pp.gh = gh; pp.gw = gw;
         if (rel_table) {
             if (nrd > 4096 || p.N > 2048 || gh * gw + 1 != p.N) { set_error("attention_f16: relative-position table mode supports nrd <= 4096, N <= 2048, N = gh*gw+1"); return DM_E_UNSUPPORTED; }
-            return launch_attn2<2>(tm, pp, stream);
+            const char *e = getenv("DEPTHMAP_B200_ATTN_GENERIC");   // read per call: the tests flip it to cover both table modes
+            const bool aligned = gw % 16 == 0 && !(e && e[0] == '1');
+            return aligned ? launch_attn2<3>(tm, pp, stream, qkv) : launch_attn2<2>(tm, pp, stream, qkv);
         }
-        return p.bias ? launch_attn2<1>(tm, pp, stream) : launch_attn2<0>(tm, pp, stream);
+        return p.bias ? launch_attn2<1>(tm, pp, stream, qkv) : launch_attn2<0>(tm, pp, stream, qkv);
     }
     static bool configured = false;
     if (!configured) {

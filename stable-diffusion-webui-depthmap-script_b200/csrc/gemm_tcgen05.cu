@@ -46,6 +46,7 @@ struct GemmParams {
     int ps_s, ps_cout, ps_h, ps_w;
     // implicit conv geometry (CONV): activations [B, H, W, Cin]; tile = hbox x wbox pixels
     int cB, cH, cW, cCin, hbox, wbox, tiles_x, tiles_y;
+    int tile_group;         // m-tiles per L2 group of the persistent tile order (set by the launcher)
 };
 
 template <int BN>
@@ -59,20 +60,49 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): two MUFU ops + a handful of FMAs instead of erff's long polynomial,
-// so the GELU epilogue of the fc1 GEMM stays hidden behind the next tile's MMAs.
+// packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100): one issue slot for two accumulator columns
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// exact-erf GELU for two columns, one MUFU each.  With u = min(|x|, 5.75):
+//     gelu(x) = max(x, 0) - u * 2^(-u Q(u) - 1),      Q(u) = -log2(erfc(u / sqrt 2)) / u
+// Q is smooth and nearly linear on [0, 5.75]; the degree-5 fit below (Lawson-weighted on the GELU error) keeps
+// |gelu - x Phi(x)| < 3.2e-7 in fp32 over all x (tests/test_gelu_formula.py checks the same numbers on
+// the host), i.e. three orders below the fp16 rounding of the stored activation.  Past the clamp u*2^(..) < 3e-8.
+__device__ __forceinline__ void gelu_erf2(float &x0, float &x1) {
+    const float u0 = fminf(fabsf(x0), 5.75f), u1 = fminf(fabsf(x1), 5.75f);
+    const uint64_t u = pack2(u0, u1);
+    uint64_t q = pack2(-2.992472582263872e-05f, -2.992472582263872e-05f);
+    q = fma2(q, u, pack2(0.0007398786256089807f, 0.0007398786256089807f));
+    q = fma2(q, u, pack2(-0.007977476343512535f, -0.007977476343512535f));
+    q = fma2(q, u, pack2(0.05323820561170578f, 0.05323820561170578f));
+    q = fma2(q, u, pack2(0.45891568064689636f, 0.45891568064689636f));
+    q = fma2(q, u, pack2(1.1511471271514893f, 1.1511471271514893f));
+    const uint64_t nu = pack2(-u0, -u1);
+    float t0, t1, e0, e1;
+    unpack2(fma2(nu, q, pack2(-1.f, -1.f)), t0, t1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+    unpack2(fma2(nu, pack2(e0, e1), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    float t, ex;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * z * -1.4426950408889634f));   // exp(-z^2)
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = fmaf(-poly * t, ex, 1.0f);           // erf(|x|/sqrt2)
-    const float hx = 0.5f * x;
-    return fmaf(fabsf(hx), e, hx);                       // 0.5 x (1 + sign(x) e) = hx + |hx| e
+    float y = x;
+    gelu_erf2(x, y);
+    return x;
 }
 
 // Epilogue for one accumulator tile: thread owns accumulator row (TMEM lane) `q*32 + lane`, walks BN columns in chunks of 32.
@@ -116,7 +146,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams &p, uint32_t tmem
             }
             if (p.act == ACT_GELU) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
             } else if (p.act == ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -220,13 +250,13 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
         float v[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            v[4 * j] = __uint_as_float(r[4 * j]) + bcur[j].x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bcur[j].y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bcur[j].z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bcur[j].w;
+            unpack2(add2(pack2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), pack2(bcur[j].x, bcur[j].y)), v[4 * j], v[4 * j + 1]);
+            unpack2(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(bcur[j].z, bcur[j].w)), v[4 * j + 2], v[4 * j + 3]);
         }
         if (p.epi == EPI_STORE_F16 || p.epi == EPI_PIXSHUF) {
             if (p.act == ACT_GELU) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
             } else if (p.act == ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -455,7 +485,10 @@ __global__ void __launch_bounds__(192, 2) gemm_tcgen05_kernel(const __grid_const
 // tile id -> (m_blk, n_blk).  Tiles are ordered in groups of `group` m-tiles; inside a group all n panels are swept with
 // m fastest.  The CTAs running concurrently therefore share ONE weight panel, and the group's A rows (group x 128 x K
 // fp16, e.g. 148 x 256 KB = 37 MB for K = 1024) stay L2-resident across the n sweep, so A is streamed from HBM once
-// instead of once per n panel (A of the fc1 GEMM at B=64 is 180 MB, larger than the 126 MB L2).
+// instead of once per n panel (A of the fc1 GEMM at B=64 is 180 MB, larger than the 126 MB L2).  `group` is chosen by
+// the launcher (pick_tile_group) so that one group's A rows stay under ~40 MB: for K = 4096 (fc2) a group of one m-tile
+// per CTA would be 155 MB and every n panel would re-stream A from HBM; with a smaller group the concurrent CTAs span
+// several n panels of the same few m-tiles instead.
 __device__ __forceinline__ void tile_coords(int tile, int num_m_tiles, int n_tiles, int group, int &m_blk, int &n_blk) {
     const int per_group = group * n_tiles;
     const int g = tile / per_group;
@@ -518,7 +551,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_persist_kerne
             int stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int m_blk, n_blk;
-                tile_coords(tile, num_m_tiles, num_tiles / num_m_tiles, (int)gridDim.x, m_blk, n_blk);
+                tile_coords(tile, num_m_tiles, num_tiles / num_m_tiles, p.tile_group, m_blk, n_blk);
                 int cb = 0, cy0 = 0, cx0 = 0;
                 if (CONV) {
                     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -575,7 +608,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_persist_kerne
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             int m_blk, n_blk;
-            tile_coords(tile, num_m_tiles, num_tiles / num_m_tiles, (int)gridDim.x, m_blk, n_blk);
+            tile_coords(tile, num_m_tiles, num_tiles / num_m_tiles, p.tile_group, m_blk, n_blk);
             long long m;
             bool row_ok;
             if (CONV) {
@@ -701,7 +734,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_2sm_kernel(co
             int stage = 0, phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 int mp, n_blk;
-                tile_coords(tile, num_m_pairs, n_tiles, num_clusters, mp, n_blk);
+                tile_coords(tile, num_m_pairs, n_tiles, p.tile_group, mp, n_blk);
                 const int m_blk = mp * 2 + (int)rank;
                 int cb = 0, cy0 = 0, cx0 = 0;
                 if (CONV) {
@@ -758,7 +791,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_2sm_kernel(co
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             const int acc = it & 1;
             int mp, n_blk;
-            tile_coords(tile, num_m_pairs, n_tiles, num_clusters, mp, n_blk);
+            tile_coords(tile, num_m_pairs, n_tiles, p.tile_group, mp, n_blk);
             const int m_blk = mp * 2 + (int)rank;
             long long m;
             bool row_ok;
@@ -860,6 +893,17 @@ static int num_sms() {
     return n;
 }
 
+// m-tiles (of `rows` rows each) per L2 group: A rows of one group (rows x K fp16 each) within ~40 MB, at least 8, at most
+// one per concurrently running CTA / cluster.  Implicit-conv tiles re-read the same pixels for all 9 taps, so their
+// footprint is rows x Cin, not rows x K.
+static int pick_tile_group(const GemmParams &p, int rows, int concurrent, bool conv) {
+    const long long bytes = (long long)rows * (conv ? p.cCin : p.K) * 2;
+    long long g = (40ll << 20) / (bytes > 0 ? bytes : 1);
+    if (g < 8) g = 8;
+    if (g > concurrent) g = concurrent;
+    return (int)g;
+}
+
 template <bool CONV>
 static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
     static bool configured = false;
@@ -870,7 +914,9 @@ static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
     const int n_tiles = p.N / PersistCfg::BN;
     const int tiles = m_tiles * n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_tcgen05_persist_kernel<CONV><<<grid, PERSIST_THREADS, PersistCfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, tiles);
+    GemmParams q = p;
+    q.tile_group = pick_tile_group(p, PersistCfg::BM, grid, CONV);
+    gemm_tcgen05_persist_kernel<CONV><<<grid, PERSIST_THREADS, PersistCfg::SMEM_BYTES, stream>>>(tmA, tmB, q, m_tiles, tiles);
     DM_LAUNCH_CHECK("gemm_tcgen05_persist_kernel");
     return DM_OK;
 }
@@ -898,7 +944,9 @@ static int launch_2sm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel<CONV>, tmA, tmB, p, m_pairs, tiles));
+    GemmParams q = p;
+    q.tile_group = pick_tile_group(p, 2 * PairCfg::BM, clusters, CONV);
+    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel<CONV>, tmA, tmB, q, m_pairs, tiles));
     return DM_OK;
 }
 

@@ -167,29 +167,27 @@ __global__ void __launch_bounds__(256) layernorm_f16_kernel(const float *__restr
 // ---------------------------------------------------------------------------------------------------------------
 // bilinear resize, NHWC fp16, align_corners=True; one thread per (output pixel, 8 channels)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const __half *__restrict__ in, int B, int Hin, int Win, int C,
-                                                                   __half *__restrict__ out, int Hout, int Wout) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c8 = C / 8;
-    const long long total = (long long)B * Hout * Wout * c8;
-    if (idx >= total) return;
-    const int c = (int)(idx % c8) * 8;
-    long long pix = idx / c8;
-    const int x = (int)(pix % Wout);
-    pix /= Wout;
-    const int y = (int)(pix % Hout);
-    const int b = (int)(pix / Hout);
-    const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
-    const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+// grid = (ceil(Wout * C/8 / 256), Hout, B): the row and image come from the block index, so the only division left is the
+// 32-bit x = t / (C/8) (the first version spent most of its time in 64-bit div/mod of a flat index and ran at a quarter
+// of the HBM rate).  One thread = 8 channels of one output pixel: four 16-byte loads (L1/L2 hits: every input pixel is
+// read by ~4 x scale^2 threads), one 16-byte store.
+__global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const __half *__restrict__ in, int Hin, int Win, int C,
+                                                                   __half *__restrict__ out, int Hout, int Wout, float sy, float sx) {
+    const int c8 = C >> 3;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= Wout * c8) return;
+    const int x = t / c8;
+    const int c = (t - x * c8) << 3;
+    const int y = blockIdx.y, b = blockIdx.z;
     const float fy = sy * (float)y, fx = sx * (float)x;
     const int y0 = min((int)fy, Hin - 1), x0 = min((int)fx, Win - 1);
     const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
     const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-    const __half *base = in + (long long)b * Hin * Win * C + c;
-    const uint4 u00 = __ldg(reinterpret_cast<const uint4 *>(base + ((long long)y0 * Win + x0) * C));
-    const uint4 u01 = __ldg(reinterpret_cast<const uint4 *>(base + ((long long)y0 * Win + x1) * C));
-    const uint4 u10 = __ldg(reinterpret_cast<const uint4 *>(base + ((long long)y1 * Win + x0) * C));
-    const uint4 u11 = __ldg(reinterpret_cast<const uint4 *>(base + ((long long)y1 * Win + x1) * C));
+    const __half *base = in + (size_t)b * Hin * Win * C + c;
+    const uint4 u00 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(y0 * Win + x0) * C));
+    const uint4 u01 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(y0 * Win + x1) * C));
+    const uint4 u10 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(y1 * Win + x0) * C));
+    const uint4 u11 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(y1 * Win + x1) * C));
     const __half2 *a = reinterpret_cast<const __half2 *>(&u00), *bq = reinterpret_cast<const __half2 *>(&u01);
     const __half2 *cq = reinterpret_cast<const __half2 *>(&u10), *d = reinterpret_cast<const __half2 *>(&u11);
     uint4 o;
@@ -202,7 +200,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const __half 
         const float r1 = hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y);
         oh[k] = __floats2half2_rn(r0, r1);
     }
-    *reinterpret_cast<uint4 *>(out + (((long long)b * Hout + y) * Wout + x) * C + c) = o;
+    __stcs(reinterpret_cast<uint4 *>(out + ((size_t)(b * Hout + y) * Wout + x) * C + c), o);
 }
 
 // single-channel fp32 resize: mode 0 = bilinear align_corners=True, mode 1 = bicubic align_corners=False (A = -0.75)
@@ -338,8 +336,13 @@ DM_EXPORT int dm_layernorm_f16(const float *x, long long rows, int C, const floa
 DM_EXPORT int dm_resize_bilinear_nhwc_f16(const void *in, int B, int Hin, int Win, int C, void *out, int Hout, int Wout, void *stream_) {
     using namespace dm;
     if (C % 8) { set_error("dm_resize_bilinear_nhwc_f16: C must be a multiple of 8"); return DM_E_INVALID; }
-    const long long total = (long long)B * Hout * Wout * (C / 8);
-    resize_bilinear_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __half *)in, B, Hin, Win, C, (__half *)out, Hout, Wout);
+    if (Hout > 65535 || B > 65535 || (long long)Hin * Win * C >= (1ll << 31) || (long long)Hout * Wout * C >= (1ll << 31)) {
+        set_error("dm_resize_bilinear_nhwc_f16: image too large for the 32-bit index path"); return DM_E_UNSUPPORTED;
+    }
+    const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+    const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+    const dim3 grid((unsigned)((Wout * (C / 8) + 255) / 256), (unsigned)Hout, (unsigned)B);
+    resize_bilinear_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const __half *)in, Hin, Win, C, (__half *)out, Hout, Wout, sy, sx);
     DM_LAUNCH_CHECK("resize_bilinear_nhwc_kernel");
     return DM_OK;
 }

@@ -127,12 +127,17 @@ def test_im2col_s2_matches_conv(cuda_device):
     assert (got - ref).abs().max().item() < 1e-3
 
 
-@pytest.mark.parametrize("B,gh,gw,H", [(1, 4, 4, 1), (2, 8, 6, 2), (2, 32, 32, 16), (1, 24, 24, 3)])
-def test_attention_relpos_table(cuda_device, B, gh, gw, H):
-    """BEiT relative-position bias generated inside the kernel vs the dense [H,N,N] gather of the reference."""
+@pytest.mark.parametrize("B,gh,gw,H", [(1, 4, 4, 1), (2, 8, 6, 2), (2, 32, 32, 16), (1, 24, 24, 3), (1, 16, 16, 2), (2, 24, 16, 3),
+                                        (1, 20, 32, 2), (1, 9, 48, 1)])
+@pytest.mark.parametrize("generic", [False, True])
+def test_attention_relpos_table(cuda_device, B, gh, gw, H, generic, monkeypatch):
+    """BEiT relative-position bias generated inside the kernel vs the dense [H,N,N] gather of the reference.  Grids whose
+    width is a multiple of 16 take the class-token-shifted tiling (contiguous table reads, SIMT class row) unless
+    DEPTHMAP_B200_ATTN_GENERIC=1; both table modes are checked on every grid."""
     import torch
     from oracle.beit_dpt import gen_relative_position_index
     L, lib = _lib()
+    monkeypatch.setenv("DEPTHMAP_B200_ATTN_GENERIC", "1" if generic else "0")
     N, C = gh * gw + 1, H * 64
     nrd = (2 * gh - 1) * (2 * gw - 1) + 3
     g = torch.Generator(device="cpu").manual_seed(gh * 100 + gw)
@@ -141,7 +146,7 @@ def test_attention_relpos_table(cuda_device, B, gh, gw, H):
     idx = gen_relative_position_index((gh, gw)).to(cuda_device)
     bias = table[idx.view(-1)].view(N, N, H).permute(2, 0, 1)
     tab_k = (table.t().contiguous() * 1.4426950408889634).float().contiguous()
-    out = torch.empty(B * N, C, dtype=torch.float16, device=cuda_device)
+    out = torch.full((B * N, C), float("nan"), dtype=torch.float16, device=cuda_device)
     rowmax = (bias.max(dim=2).values * 1.4426950408889634).float().contiguous()
     L.check(lib.dm_attention_relpos_f16(qkv.data_ptr(), B, gh, gw, H, 0.125, tab_k.data_ptr(), rowmax.data_ptr(), nrd, out.data_ptr(),
                                         L.stream_ptr()))
@@ -149,5 +154,31 @@ def test_attention_relpos_table(cuda_device, B, gh, gw, H):
     q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     s = (q * 0.125) @ k.transpose(-1, -2) + bias.unsqueeze(0)
     ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, C)
+    assert torch.isfinite(out.float()).all(), "some output rows were never written"
     err = (out.float() - ref).abs().max().item()
     assert err < 6e-3, (B, gh, gw, H, err)
+
+
+@pytest.mark.parametrize("N", [1025, 700])
+def test_attention_rising_scores_force_rescale(cuda_device, N):
+    """Keys grow along the sequence so the running row max jumps by far more than 2^8 from tile to tile: exercises the
+    lazy-rescale path (tile redone against the raised max, accumulated output and row sum scaled down)."""
+    import torch
+    L, lib = _lib()
+    B, H = 1, 2
+    C = H * 64
+    g = torch.Generator(device="cpu").manual_seed(N)
+    qkv = torch.randn(B * N, 3, H, 64, generator=g)
+    ramp = torch.linspace(0.0, 6.0, N).view(N, 1, 1)
+    qkv[:, 0] = qkv[:, 0].abs()                       # positive queries ...
+    qkv[:, 1] = qkv[:, 1].abs() * 0.2 + ramp          # ... against keys that keep growing
+    qkv = qkv.reshape(B * N, 3 * C).half().to(cuda_device)
+    out = torch.empty(B * N, C, dtype=torch.float16, device=cuda_device)
+    L.check(lib.dm_attention_f16(qkv.data_ptr(), B, N, H, 0.125, None, 0, out.data_ptr(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q * 0.125) @ k.transpose(-1, -2)
+    assert (s.max(-1).values - s[..., :128].max(-1).values).max().item() > 16        # the scenario really does rescale
+    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 6e-3, (N, err)
