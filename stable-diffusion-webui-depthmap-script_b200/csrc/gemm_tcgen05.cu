@@ -382,6 +382,70 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
     }
 }
 
+// Residual-stream epilogue (EPI_RESID_F32: X += gamma * (acc + bias)) of the persistent kernels.  The fp32 residual row
+// segments are the only long-latency operands of the whole epilogue, so they are fetched one 32-column chunk AHEAD
+// (chunk 0 even before the accumulator-ready barrier is waited on) and the proj / fc2 tiles no longer pay one exposed
+// HBM/L2 round trip per chunk.  bias and gamma are applied in the transposed (store) domain, where a lane owns four
+// fixed columns, so they cost one float4 each per chunk instead of 32 registers per thread.
+template <int BN>
+__device__ __forceinline__ void epilogue_resid_staged(const GemmParams &p, uint32_t tmem_acc, int q, int lane, long long m, bool row_ok,
+                                                      int n_base, float *stage, int col_begin, int col_end, uint64_t *bar, uint32_t parity) {
+    const int sub = lane >> 3, cc = (lane & 7) * 4;
+    // plain GEMM rows are consecutive: row rr of this warp is m - lane + rr, the store-domain rows of a lane are 4 apart.
+    // Rows past M (last m-tile only) are clamped for the prefetch so every load is unconditional; only the store is guarded.
+    // The persistent kernels require N % 256 == 0, so every column of the tile exists.
+    const long long m_first = m - lane + sub;
+    const float *xbase = p.X + n_base + cc;
+    uint32_t xoff[8];                                  // element offsets: the caller guarantees M * ldx < 2^31
+    unsigned okmask = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const long long mm = m_first + 4 * it;
+        if (mm < p.M) okmask |= 1u << it;
+        xoff[it] = (uint32_t)(mm < p.M ? mm : (long long)p.M - 1) * (uint32_t)p.ldx;
+    }
+    auto load_x = [&](float4 (&x)[8], int c0) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4 *>(xbase + xoff[it] + c0);
+    };
+    float4 xa[8], xb[8];
+    load_x(xa, col_begin);
+    mbar_wait(bar, parity);
+    tc_fence_after();
+    uint32_t rn[32];
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    tmem_ld_32x32(taddr + (uint32_t)col_begin, rn);
+    auto step = [&](int c0, float4 (&xcur)[8], float4 (&xnext)[8]) {
+        const int n0 = n_base + c0;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + n0 + cc));
+        if (p.bias) b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + cc));
+        if (c0 + 32 < col_end) load_x(xnext, c0 + 32);
+        tmem_ld_wait();
+        __syncwarp();                                  // the previous chunk's reads of the staging tile are done
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4 *>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_uint4(rn[4 * c], rn[4 * c + 1], rn[4 * c + 2], rn[4 * c + 3]);
+        if (c0 + 32 < col_end) tmem_ld_32x32(taddr + (uint32_t)(c0 + 32), rn);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = 4 * it + sub;
+            const float4 a = *reinterpret_cast<const float4 *>(stage + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+            if (!((okmask >> it) & 1u)) continue;
+            float4 x = xcur[it];
+            x.x = fmaf(g4.x, a.x + b4.x, x.x); x.y = fmaf(g4.y, a.y + b4.y, x.y);
+            x.z = fmaf(g4.z, a.z + b4.z, x.z); x.w = fmaf(g4.w, a.w + b4.w, x.w);
+            *reinterpret_cast<float4 *>(p.X + n_base + cc + xoff[it] + c0) = x;
+        }
+    };
+#pragma unroll 1
+    for (int c0 = col_begin; c0 < col_end; c0 += 64) {
+        step(c0, xa, xb);
+        if (c0 + 32 < col_end) step(c0 + 32, xb, xa);
+    }
+}
+
 template <int BN, bool CONV>
 __global__ void __launch_bounds__(192, 2) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, GemmParams p) {
@@ -516,7 +580,7 @@ struct PersistCfg {
 
 constexpr int PERSIST_THREADS = 64 + 256;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
-template <bool CONV>
+template <bool CONV, bool RESID>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB, GemmParams p,
                                                                      int num_m_tiles, int num_tiles) {
@@ -622,10 +686,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_persist_kerne
                 m = (long long)m_blk * Cfg::BM + row;
                 row_ok = m < p.M;
             }
-            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-            tc_fence_after();
-            epilogue_rows_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
-                                          staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
+            if (RESID) {     // instantiated separately: the residual-stream epilogue does not share registers with the fp16 one
+                epilogue_resid_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
+                                               staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128, &tmem_full[acc], (it >> 1) & 1);
+            } else {
+                mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+                tc_fence_after();
+                epilogue_rows_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
+                                              staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
+            }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }
@@ -695,7 +764,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive 
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-template <bool CONV>
+template <bool CONV, bool RESID>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                              const __grid_constant__ CUtensorMap tmB, GemmParams p,
                                                                              int num_m_pairs, int num_tiles) {
@@ -806,10 +875,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_2sm_kernel(co
                 m = (long long)m_blk * Cfg::BM + row;
                 row_ok = m < p.M;
             }
-            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-            tc_fence_after();
-            epilogue_rows_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
-                                          staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
+            if (RESID) {     // instantiated separately: the residual-stream epilogue does not share registers with the fp16 one
+                epilogue_resid_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
+                                               staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128, &tmem_full[acc], (it >> 1) & 1);
+            } else {
+                mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+                tc_fence_after();
+                epilogue_rows_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
+                                              staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -904,11 +978,14 @@ static int pick_tile_group(const GemmParams &p, int rows, int concurrent, bool c
     return (int)g;
 }
 
-template <bool CONV>
-static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
+// RESID instances carry only the residual-stream epilogue (EPI_RESID_F32 on a plain GEMM whose X fits 32-bit offsets)
+static bool resid_instance(const GemmParams &p, bool conv) { return !conv && p.epi == EPI_RESID_F32 && (long long)p.M * p.ldx < (1ll << 31); }
+
+template <bool CONV, bool RESID>
+static int launch_persist_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_persist_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES));
+        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_persist_kernel<CONV, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES));
         configured = true;
     }
     const int n_tiles = p.N / PersistCfg::BN;
@@ -916,16 +993,21 @@ static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
     const int grid = tiles < num_sms() ? tiles : num_sms();
     GemmParams q = p;
     q.tile_group = pick_tile_group(p, PersistCfg::BM, grid, CONV);
-    gemm_tcgen05_persist_kernel<CONV><<<grid, PERSIST_THREADS, PersistCfg::SMEM_BYTES, stream>>>(tmA, tmB, q, m_tiles, tiles);
+    gemm_tcgen05_persist_kernel<CONV, RESID><<<grid, PERSIST_THREADS, PersistCfg::SMEM_BYTES, stream>>>(tmA, tmB, q, m_tiles, tiles);
     DM_LAUNCH_CHECK("gemm_tcgen05_persist_kernel");
     return DM_OK;
 }
-
 template <bool CONV>
-static int launch_2sm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
+static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
+    if (!CONV && resid_instance(p, CONV)) return launch_persist_t<false, true>(tmA, tmB, p, m_tiles, stream);
+    return launch_persist_t<CONV, false>(tmA, tmB, p, m_tiles, stream);
+}
+
+template <bool CONV, bool RESID>
+static int launch_2sm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel<CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::SMEM_BYTES));
+        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel<CONV, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::SMEM_BYTES));
         configured = true;
     }
     const int m_pairs = (m_tiles + 1) / 2;
@@ -946,8 +1028,13 @@ static int launch_2sm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm
     cfg.numAttrs = 1;
     GemmParams q = p;
     q.tile_group = pick_tile_group(p, 2 * PairCfg::BM, clusters, CONV);
-    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel<CONV>, tmA, tmB, q, m_pairs, tiles));
+    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel<CONV, RESID>, tmA, tmB, q, m_pairs, tiles));
     return DM_OK;
+}
+template <bool CONV>
+static int launch_2sm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
+    if (!CONV && resid_instance(p, CONV)) return launch_2sm_t<false, true>(tmA, tmB, p, m_tiles, stream);
+    return launch_2sm_t<CONV, false>(tmA, tmB, p, m_tiles, stream);
 }
 
 static bool use_2sm(const GemmParams &p, int m_tiles) {
