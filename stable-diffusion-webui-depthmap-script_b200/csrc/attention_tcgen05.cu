@@ -430,22 +430,31 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
             const uint32_t ones_addr = smem_u32(sOnes);
             mbar_wait_backoff(q_full, 0);
             const int ngroups = b_active ? 2 : 1;
+            auto tile_cols = [&](int j) {
+                const int nvalid = (ALIGNED && j == num_main) ? 1 : min(AT_BKV, ntok - j * AT_BKV);
+                return (nvalid + 15) & ~15;
+            };
+            // S_g(j) = Q_g K_j^T into the S buffer of group g (free once p_full[g](j-1) has arrived)
+            auto issue_s = [&](int g, int j) {
+                const uint32_t idesc_qk = make_idesc_f16(AT_BQ, tile_cols(j), 0, 0, 0);
+                const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sKV + (j & 1) * 2 * AT_KV_BYTES));
+                const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ + g * AT_Q_BYTES));
+#pragma unroll
+                for (int k = 0; k < AT_D / 16; ++k)
+                    umma_f16(tmem_base + g * 128, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_qk, k != 0);
+                umma_commit(&s_full[g]);
+            };
+            // Issue order per group: PV_g(j) and then S_g(j+1) straight away, as soon as group g has handed over P_g(j).
+            // The two softmax groups therefore drift half a step apart: while A exponentiates, the tensor core runs B's
+            // PV / next S, and neither group waits for the OTHER group's softmax before getting its next scores.
+            mbar_wait_backoff(&kv_full[0], 0);
+            tc_fence_after();
+            for (int g = 0; g < ngroups; ++g) issue_s(g, 0);
             for (int j = 0; j < num_kv; ++j) {
                 const int s = j & 1;
-                const int nvalid = (ALIGNED && j == num_main) ? 1 : min(AT_BKV, ntok - j * AT_BKV);
-                const int ncols = (nvalid + 15) & ~15;
-                const uint32_t idesc_qk = make_idesc_f16(AT_BQ, ncols, 0, 0, 0);
-                mbar_wait_backoff(&kv_full[s], (j >> 1) & 1);
-                tc_fence_after();
-                const uint32_t sk = smem_u32(sKV + s * 2 * AT_KV_BYTES), sv = sk + AT_KV_BYTES;
-                const uint64_t kdesc = make_desc_kmajor_sw128(sk);
-                for (int g = 0; g < ngroups; ++g) {   // S_g = Q_g K_j^T  (the S buffer of group g was released by p_full[g](j-1))
-                    const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ + g * AT_Q_BYTES));
-#pragma unroll
-                    for (int k = 0; k < AT_D / 16; ++k)
-                        umma_f16(tmem_base + g * 128, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_qk, k != 0);
-                    umma_commit(&s_full[g]);
-                }
+                const int ncols = tile_cols(j);
+                const bool has_next = j + 1 < num_kv;
+                const uint32_t sv = smem_u32(sKV + s * 2 * AT_KV_BYTES) + AT_KV_BYTES;
                 for (int g = 0; g < ngroups; ++g) {   // PV_g = P_g [V_j | 1] once group g has written P_g
                     mbar_wait_backoff(&p_full[g], j & 1);
                     tc_fence_after();
@@ -457,6 +466,10 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __g
                         umma_f16(tmem_base + 256 + g * A2_PV_STRIDE, pdesc, vdesc, idesc_pv, k != 0);
                     }
                     umma_commit(&pv_full[g]);
+                    if (has_next) {
+                        if (g == 0) { mbar_wait_backoff(&kv_full[s ^ 1], ((j + 1) >> 1) & 1); tc_fence_after(); }
+                        issue_s(g, j + 1);
+                    }
                 }
                 umma_commit(&kv_empty[s]);
             }
@@ -705,31 +718,49 @@ __global__ void __launch_bounds__(256) attention_cls_row_kernel(const __half *__
         sc[k] = s;
         mx = fmaxf(mx, s);
     }
-    red[tid] = mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]); __syncthreads(); }
     mx = red[0];
-    __syncthreads();
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
     float sum = 0.f;
     for (int k = tid; k < p.N; k += 256) {
         const float pr = __half2float(__float2half_rn(ex2_approx(sc[k] - mx)));
         sc[k] = pr;
         sum += pr;
     }
-    red[tid] = sum;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
-    sum = red[0];
-    __syncthreads();
-    // weighted sum: thread = (key phase kg of 4, dim d)
-    const int d = tid & 63, kg = tid >> 6;
-    float acc = 0.f;
-    for (int k = kg; k < p.N; k += 4) acc = fmaf(sc[k], __half2float(base[(size_t)k * ld + 2 * p.C + d]), acc);
-    red[tid] = acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((tid & 31) == 0) red[8 + (tid >> 5)] = sum;
+    __syncthreads();                       // also publishes the probabilities in sc[]
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[8 + w];
+    // weighted sum: warp kg takes keys kg, kg+8, ...; lane = one pair of dims (a warp reads one 128-byte V row per key)
+    const int d2 = tid & 31, kg = tid >> 5;
+    const __half2 *vbase = reinterpret_cast<const __half2 *>(base + 2 * p.C) + d2;
+    const size_t ld2 = ld / 2;
+    float a0 = 0.f, a1 = 0.f;
+    int k = kg;
+    for (; k + 56 < p.N; k += 64) {
+        __half2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = vbase[(size_t)(k + 8 * u) * ld2];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float2 f = __half22float2(v[u]); const float pk = sc[k + 8 * u]; a0 = fmaf(pk, f.x, a0); a1 = fmaf(pk, f.y, a1); }
+    }
+    for (; k < p.N; k += 8) { const float2 f = __half22float2(vbase[(size_t)k * ld2]); const float pk = sc[k]; a0 = fmaf(pk, f.x, a0); a1 = fmaf(pk, f.y, a1); }
+    float *part = sc + ((p.N + 31) & ~31) + 256 + 64;                       // [8][64] partial outputs
+    part[kg * 64 + 2 * d2] = a0;
+    part[kg * 64 + 2 * d2 + 1] = a1;
     __syncthreads();
     if (tid < AT_D) {
-        const float v = (red[tid] + red[tid + 64] + red[tid + 128] + red[tid + 192]) / sum;
-        p.out[(size_t)b * p.N * p.C + h * AT_D + tid] = __float2half_rn(v);
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += part[w * 64 + tid];
+        p.out[(size_t)b * p.N * p.C + h * AT_D + tid] = __float2half_rn(v / sum);
     }
 }
 
@@ -746,7 +777,7 @@ static int launch_attn2(const CUtensorMap &tm, const Attn2Params &pp, cudaStream
     attention_fwd2_kernel<MODE><<<grid, A2_THREADS, smem, stream>>>(tm, pp);
     DM_LAUNCH_CHECK("attention_fwd2_kernel");
     if (MODE == 3) {
-        const int cls_smem = (((pp.a.N + 31) & ~31) + 256 + 64) * (int)sizeof(float);
+        const int cls_smem = (((pp.a.N + 31) & ~31) + 256 + 64 + 8 * 64) * (int)sizeof(float);
         attention_cls_row_kernel<<<dim3(pp.a.H, pp.a.B), 256, cls_smem, stream>>>(qkv, pp);
         DM_LAUNCH_CHECK("attention_cls_row_kernel");
     }

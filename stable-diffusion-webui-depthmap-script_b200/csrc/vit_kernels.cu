@@ -265,21 +265,19 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const __half *__restrict
 
 // MiDaS ProjectReadout input (dmidas/backbones/utils.py:28-39): row (b, p) = [x[b, 1+p, :], x[b, 0, :]] as fp16
 __global__ void __launch_bounds__(256) concat_readout_kernel(const float *__restrict__ x, int B, int N, int C, __half *__restrict__ out) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 output channels
-    const int c4 = (2 * C) / 4;
-    const long long total = (long long)B * (N - 1) * c4;
-    if (idx >= total) return;
-    const int c = (int)(idx % c4) * 4;
-    const long long row = idx / c4;
-    const int p = (int)(row % (N - 1));
-    const long long b = row / (N - 1);
-    const float *src = c < C ? x + (b * N + 1 + p) * C + c : x + (b * N) * C + (c - C);
-    const float4 v = *reinterpret_cast<const float4 *>(src);
-    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<const uint32_t *>(&h0);
-    u.y = *reinterpret_cast<const uint32_t *>(&h1);
-    *reinterpret_cast<uint2 *>(out + row * (2 * C) + c) = u;
+    // one block per output row (b, patch p): [ token (b, 1 + p) | class token (b, 0) ] as fp16; 4 channels per thread
+    const unsigned row = blockIdx.x;
+    const unsigned b = row / (unsigned)(N - 1), p = row - b * (unsigned)(N - 1);
+    const float *tok = x + ((size_t)b * N + 1 + p) * C, *cls = x + (size_t)b * N * C;
+    __half *dst = out + (size_t)row * (2 * C);
+    for (int c = threadIdx.x * 4; c < 2 * C; c += 1024) {
+        const float4 v = *reinterpret_cast<const float4 *>(c < C ? tok + c : cls + (c - C));
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t *>(&h0);
+        u.y = *reinterpret_cast<const uint32_t *>(&h1);
+        *reinterpret_cast<uint2 *>(dst + c) = u;
+    }
 }
 
 }  // namespace dm
@@ -368,8 +366,8 @@ DM_EXPORT int dm_im2col_s2_f16(const void *in, int B, int H, int W, int C, void 
 DM_EXPORT int dm_concat_readout_f16(const float *x, int B, int N, int C, void *out, void *stream_) {
     using namespace dm;
     if (C % 4) { set_error("dm_concat_readout_f16: C must be a multiple of 4"); return DM_E_INVALID; }
-    const long long total = (long long)B * (N - 1) * (2 * C / 4);
-    concat_readout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(x, B, N, C, (__half *)out);
+    if (N < 2 || (long long)B * (N - 1) >= (1ll << 31)) { set_error("dm_concat_readout_f16: bad token count"); return DM_E_INVALID; }
+    concat_readout_kernel<<<(unsigned)(B * (N - 1)), 256, 0, (cudaStream_t)stream_>>>(x, B, N, C, (__half *)out);
     DM_LAUNCH_CHECK("concat_readout_kernel");
     return DM_OK;
 }
