@@ -212,11 +212,17 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams &p, uint32_t tmem
 // chunk through a private 4 KB smem buffer (16-byte chunks XOR-swizzled by row, conflict-free both ways) and then
 // 8 lanes cover one row's 128 B, so a warp-level access touches 4 full lines: 8x fewer LSU line transactions for
 // the fp32 residual-stream read-modify-write, 4x fewer for fp16 stores, and fp16 residual reads ride the same pattern.
-template <int BN>
+template <int BN, int SPEC = 0>
 __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32_t tmem_acc, int q, int lane, long long m, bool row_ok,
                                                      int n_base, float *stage, int col_begin = 0, int col_end = BN) {
     const int sub = lane >> 3, cc = (lane & 7) * 4;
-    const bool has_bias = p.bias != nullptr;
+    // SPEC > 0: compile-time epilogue (1 = fp16 store + bias, 2 = the same + GELU; no residual inputs, no ReLU copy): the
+    // mode tests below fold away instead of being re-evaluated (constant-bank loads, branches) for every chunk and row
+    const int epi = SPEC ? (int)EPI_STORE_F16 : p.epi;
+    const int act = SPEC == 2 ? (int)ACT_GELU : (SPEC == 1 ? (int)ACT_NONE : p.act);
+    const __half *R = SPEC ? nullptr : p.R, *R2 = SPEC ? nullptr : p.R2;
+    __half *C2 = SPEC ? nullptr : p.C2;
+    const bool has_bias = SPEC ? true : p.bias != nullptr;
     // bias (thread = row domain: all 32 columns of the chunk) is prefetched one chunk ahead so its L2 latency hides
     // behind the previous chunk's work instead of sitting between tcgen05.ld and the first FADD
     float4 bcur[8];
@@ -241,7 +247,7 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
             for (int j = 0; j < 8; ++j) bnext[j] = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + 32 + 4 * j));
         }
         float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.epi == EPI_RESID_F32 && col_ok) g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + n0 + cc));
+        if (epi == EPI_RESID_F32 && col_ok) g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + n0 + cc));
         uint32_t r[32];
         tmem_ld_wait();
 #pragma unroll
@@ -253,16 +259,16 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
             unpack2(add2(pack2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), pack2(bcur[j].x, bcur[j].y)), v[4 * j], v[4 * j + 1]);
             unpack2(add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(bcur[j].z, bcur[j].w)), v[4 * j + 2], v[4 * j + 3]);
         }
-        if (p.epi == EPI_STORE_F16 || p.epi == EPI_PIXSHUF) {
-            if (p.act == ACT_GELU) {
+        if (epi == EPI_STORE_F16 || epi == EPI_PIXSHUF) {
+            if (act == ACT_GELU) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
-            } else if (p.act == ACT_RELU) {
+            } else if (act == ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
         }
-        const bool f16_out = p.epi == EPI_STORE_F16 || p.epi == EPI_PIXSHUF;
+        const bool f16_out = epi == EPI_STORE_F16 || epi == EPI_PIXSHUF;
         const int hsel = ((c0 - col_begin) >> 5) & 1;          // fp16 outputs: two 32-column chunks share one 64-column round
         if (f16_out) {
             // row `lane` of the staging tile holds 64 halves (128 B); this chunk fills 16-byte slots hsel*4 .. hsel*4+3
@@ -294,7 +300,7 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
         const int nr0 = f16_out ? n0 - hsel * 32 : n0;          // first column of this round
         const int ncols_round = f16_out ? (hsel + 1) * 32 : 32;
         int ps_i = 0, ps_j = 0, ps_co = 0;
-        if (p.epi == EPI_PIXSHUF) { const int ij = nr0 / p.ps_cout; ps_co = nr0 % p.ps_cout; ps_i = ij / p.ps_s; ps_j = ij % p.ps_s; }
+        if (epi == EPI_PIXSHUF) { const int ij = nr0 / p.ps_cout; ps_co = nr0 % p.ps_cout; ps_i = ij / p.ps_s; ps_j = ij % p.ps_s; }
         // ---- transposed domain: 8 lanes cover one row's 128 B; all global loads of the chunk are issued first ----
         long long m_r[8];
         bool ok[8];
@@ -304,7 +310,7 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
             m_r[it] = __shfl_sync(0xffffffffu, m, rr);
             ok[it] = __shfl_sync(0xffffffffu, (int)row_ok, rr) != 0 && (f16_out || col_ok);
         }
-        if (p.epi == EPI_RESID_F32) {
+        if (epi == EPI_RESID_F32) {
             float4 x4[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it)
@@ -318,7 +324,7 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
                 x.x = fmaf(g4.x, a.x, x.x); x.y = fmaf(g4.y, a.y, x.y); x.z = fmaf(g4.z, a.z, x.z); x.w = fmaf(g4.w, a.w, x.w);
                 *reinterpret_cast<float4 *>(p.X + m_r[it] * p.ldx + n0 + cc) = x;
             }
-        } else if (p.epi == EPI_STORE_F32) {
+        } else if (epi == EPI_STORE_F32) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int rr = 4 * it + sub;
@@ -332,13 +338,13 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {      // two batches of four rows keep the residual prefetch at 32 registers
                 uint4 r1[4], r2[4];
-                if (p.R) {
+                if (R) {
 #pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) { const int it = hb * 4 + i4; if (ok[it] && lane_ok) r1[i4] = __ldg(reinterpret_cast<const uint4 *>(p.R + m_r[it] * p.ldr + nr0 + ch * 8)); }
+                    for (int i4 = 0; i4 < 4; ++i4) { const int it = hb * 4 + i4; if (ok[it] && lane_ok) r1[i4] = __ldg(reinterpret_cast<const uint4 *>(R + m_r[it] * p.ldr + nr0 + ch * 8)); }
                 }
-                if (p.R2) {
+                if (R2) {
 #pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) { const int it = hb * 4 + i4; if (ok[it] && lane_ok) r2[i4] = __ldg(reinterpret_cast<const uint4 *>(p.R2 + m_r[it] * p.ldr2 + nr0 + ch * 8)); }
+                    for (int i4 = 0; i4 < 4; ++i4) { const int it = hb * 4 + i4; if (ok[it] && lane_ok) r2[i4] = __ldg(reinterpret_cast<const uint4 *>(R2 + m_r[it] * p.ldr2 + nr0 + ch * 8)); }
                 }
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
@@ -346,18 +352,18 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
                     const int rr = 4 * it + sub;
                     uint4 u = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(stage) + rr * 128 + ((ch ^ (rr & 7)) << 4));
                     if (!ok[it] || !lane_ok) continue;
-                    if (p.R || p.R2) {
+                    if (R || R2) {
                         __half2 *h2 = reinterpret_cast<__half2 *>(&u);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             float2 f = __half22float2(h2[k]);
-                            if (p.R) { const float2 a = __half22float2(reinterpret_cast<const __half2 *>(&r1[i4])[k]); f.x += a.x; f.y += a.y; }
-                            if (p.R2) { const float2 a = __half22float2(reinterpret_cast<const __half2 *>(&r2[i4])[k]); f.x += a.x; f.y += a.y; }
+                            if (R) { const float2 a = __half22float2(reinterpret_cast<const __half2 *>(&r1[i4])[k]); f.x += a.x; f.y += a.y; }
+                            if (R2) { const float2 a = __half22float2(reinterpret_cast<const __half2 *>(&r2[i4])[k]); f.x += a.x; f.y += a.y; }
                             h2[k] = __floats2half2_rn(f.x, f.y);
                         }
                     }
                     __half *dst;
-                    if (p.epi == EPI_PIXSHUF) {
+                    if (epi == EPI_PIXSHUF) {
                         const int s_ = p.ps_s;
                         const long long bb = m_r[it] / ((long long)p.ps_h * p.ps_w);
                         const int rem = (int)(m_r[it] % ((long long)p.ps_h * p.ps_w));
@@ -367,12 +373,12 @@ __device__ __forceinline__ void epilogue_rows_staged(const GemmParams &p, uint32
                         dst = p.C + m_r[it] * p.ldc + nr0 + ch * 8;
                     }
                     *reinterpret_cast<uint4 *>(dst) = u;
-                    if (p.C2 && p.epi != EPI_PIXSHUF) {
+                    if (C2 && epi != EPI_PIXSHUF) {
                         const __half2 z = __float2half2_rn(0.f);
                         __half2 *h2 = reinterpret_cast<__half2 *>(&u);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) h2[k] = __hmax2(h2[k], z);
-                        *reinterpret_cast<uint4 *>(p.C2 + m_r[it] * p.ldc + nr0 + ch * 8) = u;
+                        *reinterpret_cast<uint4 *>(C2 + m_r[it] * p.ldc + nr0 + ch * 8) = u;
                     }
                 }
             }
@@ -580,7 +586,7 @@ struct PersistCfg {
 
 constexpr int PERSIST_THREADS = 64 + 256;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
-template <bool CONV, bool RESID>
+template <bool CONV, int SPEC>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB, GemmParams p,
                                                                      int num_m_tiles, int num_tiles) {
@@ -686,14 +692,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_persist_kerne
                 m = (long long)m_blk * Cfg::BM + row;
                 row_ok = m < p.M;
             }
-            if (RESID) {     // instantiated separately: the residual-stream epilogue does not share registers with the fp16 one
+            if (SPEC == 3) {     // instantiated separately: the residual-stream epilogue does not share registers with the fp16 one
                 epilogue_resid_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
                                                staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128, &tmem_full[acc], (it >> 1) & 1);
             } else {
                 mbar_wait(&tmem_full[acc], (it >> 1) & 1);
                 tc_fence_after();
-                epilogue_rows_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
-                                              staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
+                epilogue_rows_staged<Cfg::BN, SPEC == 3 ? 0 : SPEC>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
+                                                                    staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
@@ -764,7 +770,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive 
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-template <bool CONV, bool RESID>
+template <bool CONV, int SPEC>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                              const __grid_constant__ CUtensorMap tmB, GemmParams p,
                                                                              int num_m_pairs, int num_tiles) {
@@ -875,14 +881,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tcgen05_2sm_kernel(co
                 m = (long long)m_blk * Cfg::BM + row;
                 row_ok = m < p.M;
             }
-            if (RESID) {     // instantiated separately: the residual-stream epilogue does not share registers with the fp16 one
+            if (SPEC == 3) {     // instantiated separately: the residual-stream epilogue does not share registers with the fp16 one
                 epilogue_resid_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
                                                staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128, &tmem_full[acc], (it >> 1) & 1);
             } else {
                 mbar_wait(&tmem_full[acc], (it >> 1) & 1);
                 tc_fence_after();
-                epilogue_rows_staged<Cfg::BN>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
-                                              staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
+                epilogue_rows_staged<Cfg::BN, SPEC == 3 ? 0 : SPEC>(p, tmem_base + (uint32_t)(acc * Cfg::BN), q, lane, m, row_ok, n_blk * Cfg::BN,
+                                                                    staging + (warp - 2) * 1024, ehalf * 128, ehalf * 128 + 128);
             }
             tc_fence_before();
             __syncwarp();
@@ -978,14 +984,23 @@ static int pick_tile_group(const GemmParams &p, int rows, int concurrent, bool c
     return (int)g;
 }
 
-// RESID instances carry only the residual-stream epilogue (EPI_RESID_F32 on a plain GEMM whose X fits 32-bit offsets)
-static bool resid_instance(const GemmParams &p, bool conv) { return !conv && p.epi == EPI_RESID_F32 && (long long)p.M * p.ldx < (1ll << 31); }
+// Epilogue specialisation of the persistent kernels (plain GEMMs only): 3 = residual stream (EPI_RESID_F32, X within
+// 32-bit offsets), 1 = fp16 store + bias, 2 = fp16 store + bias + GELU, 0 = everything else (runtime modes)
+static int epilogue_spec(const GemmParams &p, bool conv) {
+    if (conv) return 0;
+    if (p.epi == EPI_RESID_F32 && (long long)p.M * p.ldx < (1ll << 31)) return 3;
+    if (p.epi == EPI_STORE_F16 && p.bias && !p.R && !p.R2 && !p.C2) {
+        if (p.act == ACT_NONE) return 1;
+        if (p.act == ACT_GELU) return 2;
+    }
+    return 0;
+}
 
-template <bool CONV, bool RESID>
+template <bool CONV, int SPEC>
 static int launch_persist_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_persist_kernel<CONV, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES));
+        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_persist_kernel<CONV, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES));
         configured = true;
     }
     const int n_tiles = p.N / PersistCfg::BN;
@@ -993,21 +1008,25 @@ static int launch_persist_t(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
     const int grid = tiles < num_sms() ? tiles : num_sms();
     GemmParams q = p;
     q.tile_group = pick_tile_group(p, PersistCfg::BM, grid, CONV);
-    gemm_tcgen05_persist_kernel<CONV, RESID><<<grid, PERSIST_THREADS, PersistCfg::SMEM_BYTES, stream>>>(tmA, tmB, q, m_tiles, tiles);
+    gemm_tcgen05_persist_kernel<CONV, SPEC><<<grid, PERSIST_THREADS, PersistCfg::SMEM_BYTES, stream>>>(tmA, tmB, q, m_tiles, tiles);
     DM_LAUNCH_CHECK("gemm_tcgen05_persist_kernel");
     return DM_OK;
 }
 template <bool CONV>
 static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
-    if (!CONV && resid_instance(p, CONV)) return launch_persist_t<false, true>(tmA, tmB, p, m_tiles, stream);
-    return launch_persist_t<CONV, false>(tmA, tmB, p, m_tiles, stream);
+    switch (epilogue_spec(p, CONV)) {
+        case 3: return launch_persist_t<false, 3>(tmA, tmB, p, m_tiles, stream);
+        case 2: return launch_persist_t<false, 2>(tmA, tmB, p, m_tiles, stream);
+        case 1: return launch_persist_t<false, 1>(tmA, tmB, p, m_tiles, stream);
+        default: return launch_persist_t<CONV, 0>(tmA, tmB, p, m_tiles, stream);
+    }
 }
 
-template <bool CONV, bool RESID>
+template <bool CONV, int SPEC>
 static int launch_2sm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel<CONV, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::SMEM_BYTES));
+        DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel<CONV, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::SMEM_BYTES));
         configured = true;
     }
     const int m_pairs = (m_tiles + 1) / 2;
@@ -1028,13 +1047,17 @@ static int launch_2sm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const Ge
     cfg.numAttrs = 1;
     GemmParams q = p;
     q.tile_group = pick_tile_group(p, 2 * PairCfg::BM, clusters, CONV);
-    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel<CONV, RESID>, tmA, tmB, q, m_pairs, tiles));
+    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel<CONV, SPEC>, tmA, tmB, q, m_pairs, tiles));
     return DM_OK;
 }
 template <bool CONV>
 static int launch_2sm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
-    if (!CONV && resid_instance(p, CONV)) return launch_2sm_t<false, true>(tmA, tmB, p, m_tiles, stream);
-    return launch_2sm_t<CONV, false>(tmA, tmB, p, m_tiles, stream);
+    switch (epilogue_spec(p, CONV)) {
+        case 3: return launch_2sm_t<false, 3>(tmA, tmB, p, m_tiles, stream);
+        case 2: return launch_2sm_t<false, 2>(tmA, tmB, p, m_tiles, stream);
+        case 1: return launch_2sm_t<false, 1>(tmA, tmB, p, m_tiles, stream);
+        default: return launch_2sm_t<CONV, 0>(tmA, tmB, p, m_tiles, stream);
+    }
 }
 
 static bool use_2sm(const GemmParams &p, int m_tiles) {
