@@ -819,7 +819,10 @@ __global__ void __launch_bounds__(A3_THREADS, 1) attention_fwd3_kernel(const __g
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+        // the register pool of the CTA is what it was launched with (640 x 96); the producer warpgroup hands back
+        // 128 x (96 - 24), which lets the four softmax warpgroups grow to 112 (4 x 128 x 16 = 8192 <= 9216) - asking for more
+        // than the pool holds blocks forever
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int idx = warp - 4;
         const int g = idx >> 3, hh = (idx >> 2) & 1, q = idx & 3;
         if (!(g == 1 && !b_active)) {
@@ -988,13 +991,15 @@ __global__ void __launch_bounds__(A3_THREADS, 1) attention_fwd3_kernel(const __g
                         }
                     }
                 }
-                mx_rel = pair_max(mx_rel);                  // both threads of the row take the same decision
+                mx_rel = pair_max(mx_rel);                  // both threads of the row see the same value ...
                 const bool need = mx_rel > 8.0f;
-                if (!need) break;                           // (the pair loops together: the decision is row-wide)
-                const float alpha = ex2_approx(-mx_rel);
+                if (!__any_sync(0xffffffffu, need)) break;  // ... so both warps of the pair take the same (warp-uniform) decision
+                if (need) {
+                    const float alpha = ex2_approx(-mx_rel);
 #pragma unroll
-                for (int d = 0; d <= AT_D / 2; ++d) o[d] *= alpha;
-                m_run += mx_rel;
+                    for (int d = 0; d <= AT_D / 2; ++d) o[d] *= alpha;
+                    m_run += mx_rel;
+                }
             }
             tc_fence_before();
             fence_proxy_async();

@@ -61,6 +61,43 @@ __device__ __forceinline__ void normal_from_grad(int gx, int gy, int sgn, uint8_
     r = qx; g = qy; b = qz;
 }
 
+// ---- lean variant of normal_from_grad for the W % 8 == 0 kernel: no XU-pipe conversions (int->float and floor through
+// the 2^23 magic number), a tighter "safe" band (the fp32 value carries < 2^-13 absolute error on the [0,256] scale —
+// rsqrt.approx 2 ulp, two multiplies, one fma at magnitude <= 256 — so 2^-10 still leaves a 8x margin) so that only
+// ~0.6% of the pixels, i.e. ~1 warp in 6 instead of 1 in 2, takes the fp64 detour.
+__device__ __forceinline__ float int_to_float_exact(int a) {        // |a| < 2^22
+    return __int_as_float(0x4B400000 + a) - 12582912.0f;
+}
+__device__ __forceinline__ uint32_t floor_u8_if_safe(float v, bool &safe) {     // 0 <= v <= 256.01
+    const float t = v + 8388608.0f;                 // round to nearest integer, result in the low mantissa bits
+    const float d = v - (t - 8388608.0f);
+    safe = fabsf(d) > 0.0009765625f;
+    int q = (__float_as_int(t) & 0x1ff) - (d < 0.f ? 1 : 0);
+    return (uint32_t)min(q, 255);
+}
+__device__ __forceinline__ uint32_t normal_rgb_packed(int gx, int gy, int sgn) {   // r | g << 8 | b << 16
+    const int ax = sgn * gx, ay = -sgn * gy;
+    const float fx = int_to_float_exact(ax) * 0.00390625f, fy = int_to_float_exact(ay) * 0.00390625f;
+    const float s = fmaf(fx, fx, fmaf(fy, fy, 1.0f));
+    const float rs = rsqrtf(s);
+    const float r128 = rs * 128.0f;
+    bool sx, sy, sz;
+    uint32_t qx = floor_u8_if_safe(fmaf(fx, r128, 128.0f), sx);
+    uint32_t qy = floor_u8_if_safe(fmaf(fy, r128, 128.0f), sy);
+    uint32_t qz = floor_u8_if_safe(r128 + 128.0f, sz);
+    if (ax == 0) { qx = 128; sx = true; }
+    if (ay == 0) { qy = 128; sy = true; }
+    if ((ax | ay) == 0) { qz = 255; sz = true; }
+    if (!(sx && sy && sz)) {
+        const double dx = (double)ax * 0.00390625, dy = (double)ay * 0.00390625;
+        const double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 1.0));
+        if (!sx) qx = quant_exact(dx, n);
+        if (!sy) qy = quant_exact(dy, n);
+        if (!sz) qz = quant_exact(1.0, n);
+    }
+    return qx | (qy << 8) | (qz << 16);
+}
+
 constexpr int NM_TX = 128;  // threads per block, 4 px per thread -> 512 px of one row per block
 constexpr int NM_PX = 4;
 
@@ -107,6 +144,66 @@ __global__ void __launch_bounds__(NM_TX) normalmap_sobel3_kernel(const uint16_t 
     }
     const int tail0 = h + nwords * 4;
     if ((int)threadIdx.x < nbytes - tail0) dst[tail0 + threadIdx.x] = stage[tail0 + threadIdx.x];
+}
+
+// W % 8 == 0: the three depth rows of the block (512 + 2 halo pixels each) are staged in shared memory with 16-byte
+// loads, every thread turns 4 pixels into three packed 32-bit words, and the block's 1536 output bytes leave as 8-byte
+// stores.  ~50 instructions per pixel instead of ~190 (per-load border reflection, byte-wise staging and XU-pipe
+// conversions were what made the first version issue-bound at 12% of the HBM rate).
+__global__ void __launch_bounds__(NM_TX) normalmap_sobel3_w8_kernel(const uint16_t *__restrict__ depth, int H, int W, int sgn,
+                                                                    uint8_t *__restrict__ out) {
+    constexpr int SPAN = NM_TX * NM_PX;                       // 512 pixels
+    __shared__ __align__(16) uint16_t rows[3][SPAN + 8];      // element e of a row = pixel x_blk - 1 + (e - 3)... see ROFF
+    __shared__ __align__(16) uint32_t words[SPAN * 3 / 4];
+    constexpr int ROFF = 4;                                   // pixel x_blk sits at element ROFF (8-byte aligned), halo at ROFF-1
+    const int b = blockIdx.z, y = blockIdx.y;
+    const int x_blk = blockIdx.x * SPAN;
+    const uint16_t *img = depth + (int64_t)b * H * W;
+    const int ys[3] = {reflect101(y - 1, H), y, reflect101(y + 1, H)};
+    const int npx = min(SPAN, W - x_blk);                     // multiple of 8
+    for (int i = threadIdx.x; i < 3 * (SPAN / 8); i += NM_TX) {
+        const int r = i / (SPAN / 8), v = i - r * (SPAN / 8);
+        if (v * 8 < npx) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(img + (int64_t)ys[r] * W + x_blk + v * 8));
+            *reinterpret_cast<uint2 *>(&rows[r][ROFF + v * 8]) = make_uint2(u.x, u.y);
+            *reinterpret_cast<uint2 *>(&rows[r][ROFF + v * 8 + 4]) = make_uint2(u.z, u.w);
+        }
+    }
+    if (threadIdx.x < 6) {                                    // the two halo pixels of each row (border: reflect 101)
+        const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
+        const int xx = right ? x_blk + npx : x_blk - 1;
+        rows[r][right ? ROFF + npx : ROFF - 1] = __ldg(img + (int64_t)ys[r] * W + reflect101(xx, W));
+    }
+    __syncthreads();
+    const int px0 = threadIdx.x * NM_PX;
+    if (px0 < npx) {
+        int c[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            // elements ROFF-1+px0 .. ROFF+4+px0: one 2-byte, one 8-byte and one 2-byte access around the aligned quad
+            const uint16_t *rp = &rows[r][ROFF + px0];
+            const uint2 m = *reinterpret_cast<const uint2 *>(rp);
+            c[r][0] = rp[-1];
+            c[r][1] = m.x & 0xffff; c[r][2] = m.x >> 16; c[r][3] = m.y & 0xffff; c[r][4] = m.y >> 16;
+            c[r][5] = rp[4];
+        }
+        uint32_t px[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gx = (c[0][i + 2] - c[0][i]) + 2 * (c[1][i + 2] - c[1][i]) + (c[2][i + 2] - c[2][i]);
+            const int gy = (c[2][i] - c[0][i]) + 2 * (c[2][i + 1] - c[0][i + 1]) + (c[2][i + 2] - c[0][i + 2]);
+            px[i] = normal_rgb_packed(gx, gy, sgn);
+        }
+        words[threadIdx.x * 3 + 0] = px[0] | (px[1] << 24);
+        words[threadIdx.x * 3 + 1] = (px[1] >> 8) | (px[2] << 16);
+        words[threadIdx.x * 3 + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
+    __syncthreads();
+    // row pitch W * 3 and the block offset 1536 k are multiples of 8 (W % 8 == 0), not of 16: 8-byte stores
+    uint8_t *dst = out + ((int64_t)b * H + y) * (int64_t)W * 3 + (int64_t)x_blk * 3;
+    const int nvec = npx * 3 / 8;                             // npx % 8 == 0 -> exact
+    for (int i = threadIdx.x; i < nvec; i += NM_TX)
+        *reinterpret_cast<uint2 *>(dst + i * 8) = *reinterpret_cast<const uint2 *>(&words[i * 2]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -264,7 +361,8 @@ extern "C" __attribute__((visibility("default"))) int dm_normalmap(const uint16_
     if (fast_path(pre_blur, sobel, post_blur)) {
         dim3 grid((W + NM_TX * NM_PX - 1) / (NM_TX * NM_PX), H, B);
         if (H > 65535 || B > 65535) { set_error("dm_normalmap: H or B too large"); return DM_E_UNSUPPORTED; }
-        normalmap_sobel3_kernel<<<grid, NM_TX, 0, stream>>>(depth, H, W, invert ? 1 : -1, rgb_out);
+        if (W % 8 == 0) normalmap_sobel3_w8_kernel<<<grid, NM_TX, 0, stream>>>(depth, H, W, invert ? 1 : -1, rgb_out);
+        else normalmap_sobel3_kernel<<<grid, NM_TX, 0, stream>>>(depth, H, W, invert ? 1 : -1, rgb_out);
         DM_LAUNCH_CHECK("normalmap_sobel3_kernel");
         return DM_OK;
     }

@@ -318,8 +318,8 @@ class DepthAnythingV2Engine:
             b[f'u{i}'] = h16(B, s[0], s[1], Fp)      # RCU2 output
         up = [sizes[2], sizes[1], sizes[0], (sizes[0][0] * 2, sizes[0][1] * 2)]  # target size of refinenet4..1
         b['up_sizes'] = up
-        b['v'] = [h16(B, s[0], s[1], Fp) for s in up]      # interpolated
-        b['path'] = [h16(B, s[0], s[1], Fp) for s in up]   # after out_conv
+        b['v'] = [h16(B, s[0], s[1], Fp) for s in (sizes[3], sizes[2], sizes[1], sizes[0])]   # out_conv output, before the up-sample
+        b['path'] = [h16(B, s[0], s[1], Fp) for s in up]   # refinenet output (up-sampled)
         b['oc1'] = h16(B, up[3][0], up[3][1], self.F2p)
         b['oc1u'] = h16(B, nh, nw, self.F2p)
         b['d'] = torch.empty(B, nh, nw, dtype=torch.float32, device=dev)
@@ -386,14 +386,16 @@ class DepthAnythingV2Engine:
         rs = [b['r'][0], b['r'][1], r2, b['r'][3]]
         for i in range(4):  # layer{i}_rn (no bias) -> l_i and relu(l_i)
             ops.conv3x3(rs[i], B, sizes[i][0], sizes[i][1], self.ocp[i], w[f'rn{i}_w'], Fp, C=b['l'][i], C2=b['lr'][i])
-        # refinenet4: resConfUnit2(l4) -> resize -> out_conv
+        # refinenet4: resConfUnit2(l4) -> resize -> out_conv.  The 1x1 out_conv (+ bias) commutes with the bilinear
+        # interpolation (a per-pixel channel mix against per-channel spatial weights that sum to one), so it runs BEFORE the
+        # up-sample: a quarter of the MACs and no full-resolution intermediate (dmidas/blocks.py:425-437 has it after).
         s3 = sizes[3]
         ops.conv3x3(b['lr'][3], B, s3[0], s3[1], Fp, w['rf4_u2c1_w'], Fp, act=A.ACT_RELU, bias=w['rf4_u2c1_b'], C=b['t3'])
         ops.conv3x3(b['t3'], B, s3[0], s3[1], Fp, w['rf4_u2c2_w'], Fp, bias=w['rf4_u2c2_b'], C=b['u3'], R=b['l'][3])
         up = b['up_sizes']
-        ops.resize_nhwc(b['u3'], B, s3[0], s3[1], Fp, b['v'][0], up[0][0], up[0][1])
-        ops.gemm(b['v'][0], Fp, w['rf4_out_w'], Fp, B * up[0][0] * up[0][1], Fp, Fp, bias=w['rf4_out_b'], C=b['path'][0], ldc=Fp)
-        # refinenet3, 2, 1: output = path + RCU1(l_i); output = RCU2(output); resize; out_conv
+        ops.gemm(b['u3'], Fp, w['rf4_out_w'], Fp, B * s3[0] * s3[1], Fp, Fp, bias=w['rf4_out_b'], C=b['v'][0], ldc=Fp)
+        ops.resize_nhwc(b['v'][0], B, s3[0], s3[1], Fp, b['path'][0], up[0][0], up[0][1])
+        # refinenet3, 2, 1: output = path + RCU1(l_i); output = RCU2(output); out_conv; resize (commuted, see above)
         for step, (li, rf) in enumerate(((2, 3), (1, 2), (0, 1))):
             s = sizes[li]
             path = b['path'][step]
@@ -403,8 +405,8 @@ class DepthAnythingV2Engine:
             ops.conv3x3(b[f'or{li}'], B, s[0], s[1], Fp, w[f'rf{rf}_u2c1_w'], Fp, act=A.ACT_RELU, bias=w[f'rf{rf}_u2c1_b'], C=b[f't{li}'])
             ops.conv3x3(b[f't{li}'], B, s[0], s[1], Fp, w[f'rf{rf}_u2c2_w'], Fp, bias=w[f'rf{rf}_u2c2_b'], C=b[f'u{li}'], R=b[f'o{li}'])
             t = up[step + 1]
-            ops.resize_nhwc(b[f'u{li}'], B, s[0], s[1], Fp, b['v'][step + 1], t[0], t[1])
-            ops.gemm(b['v'][step + 1], Fp, w[f'rf{rf}_out_w'], Fp, B * t[0] * t[1], Fp, Fp, bias=w[f'rf{rf}_out_b'], C=b['path'][step + 1], ldc=Fp)
+            ops.gemm(b[f'u{li}'], Fp, w[f'rf{rf}_out_w'], Fp, B * s[0] * s[1], Fp, Fp, bias=w[f'rf{rf}_out_b'], C=b['v'][step + 1], ldc=Fp)
+            ops.resize_nhwc(b['v'][step + 1], B, s[0], s[1], Fp, b['path'][step + 1], t[0], t[1])
         t = up[3]
         ops.conv3x3(b['path'][3], B, t[0], t[1], Fp, w['oc1_w'], self.F2p, bias=w['oc1_b'], C=b['oc1'])
         ops.resize_nhwc(b['oc1'], B, t[0], t[1], self.F2p, b['oc1u'], nh, nw)

@@ -118,7 +118,7 @@ def test_stereo_non_u16_depth_and_api_edges(cuda_device):
     assert create_stereoimages(img, dep, 2.5, modes="top-bottom")[0].size == (40, 24)
 
 
-@pytest.mark.parametrize("hw", [(64, 64), (37, 518), (3, 5), (1, 9), (9, 1), (50, 2051)])
+@pytest.mark.parametrize("hw", [(64, 64), (37, 518), (3, 5), (1, 9), (9, 1), (50, 2051), (40, 520), (16, 1032), (33, 8), (5, 512)])
 def test_normalmap_batch_vs_oracle(cuda_device, hw):
     from depthmap_b200.normalmap_generation import create_normalmap_batch
     from oracle import normalmap as onm
@@ -131,6 +131,20 @@ def test_normalmap_batch_vs_oracle(cuda_device, hw):
         for b in range(3):
             want = onm.create_normalmap(deps[b], pb, sb, qb, inv, return_array=True)
             assert np.array_equal(got[b], want), (hw, b, pb, sb, qb, inv, int((got[b] != want).sum()))
+
+
+def test_normalmap_sobel3_full_2048_bit_exact(cuda_device):
+    """Every pixel of two 2048^2 maps (smooth and noisy, both signs) through the fused Sobel-3 kernel against the oracle:
+    8M+ pixels exercise the fp32-screen / fp64-detour decision of the fast path at its truncation boundaries."""
+    from depthmap_b200.normalmap_generation import create_normalmap_batch
+    from oracle import normalmap as onm
+    deps = [synth_depth_u16(2048, 2048, 11), noise_depth_u16(2048, 2048, 12)]
+    t = _u16_to_cuda(np.stack(deps), cuda_device)
+    for inv in (False, True):
+        got = create_normalmap_batch(t, None, 3, None, inv).cpu().numpy()
+        for b in range(2):
+            want = onm.create_normalmap(deps[b], None, 3, None, inv, return_array=True)
+            assert np.array_equal(got[b], want), (b, inv, int((got[b] != want).sum()))
 
 
 @pytest.mark.parametrize("hw", [(48, 64), (37, 518), (1, 1), (7, 3)])
