@@ -170,6 +170,41 @@ class Stereo2048:
         return 1, time.perf_counter() - t0
 
 
+def host_threads():
+    """Threads the CPU arm may really use: scheduler affinity and the cgroup CPU quota, not the machine's core count."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def pick_torch_threads(limit):
+    """torch's intra-op pool is fastest well below the hardware thread count on big hosts (SMT siblings, NUMA): time one
+    fp32 GEMM at a few pool sizes and keep the best, so the CPU arm is not handicapped by oversubscription."""
+    import torch
+    a = torch.randn(1536, 1536)
+    best, best_t = limit, None
+    for n in sorted({limit, min(limit, 64), min(limit, 32), min(limit, 16), min(limit, 8)}, reverse=True):
+        torch.set_num_threads(n)
+        a @ a
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ a
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t * 0.9:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 class GraphedStep:
     """Captures one full step (every kernel launch of the hot path, allocations included) into a CUDA graph and replays
     it: same kernels, same work per step, without ~700 host-side launches per step.  Falls back to eager if capture fails."""
@@ -220,8 +255,8 @@ def run_reference(args, rank, world):
     oracle.build()
     wl_cls = WORKLOADS[args.workload]
     wl = wl_cls.__new__(wl_cls)
-    cores = os.cpu_count() or 1
     import torch
+    cores = pick_torch_threads(host_threads())
     rgb, pred = make_images(1, wl_cls.H, wl_cls.W, 0)
     wl.rgb_h, wl.pred_h = torch.from_numpy(rgb), torch.from_numpy(pred)
     # every step is one image through the CPU path; the whole run is held to ~4 minutes: if the first (untimed) image
@@ -373,7 +408,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
-            cores = os.cpu_count() or 1
+            cores = pick_torch_threads(host_threads())
             wl.cpu_sample(cores)
             n, dt = wl.cpu_sample(cores)
             line["cpu_baseline"] = {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port",
