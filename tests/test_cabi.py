@@ -65,7 +65,7 @@ def test_product_never_imports_oracle():
                 assert "liboracle" not in txt, f
 
 
-def test_no_vimnmx_predicate_output_in_sass():
+def test_no_vimnmx_predicate_output_in_sass(built):
     """CUDA 12.9 ptxas for sm_100a miscompiles `min/max` followed by an equality test on the same operands (fused into
     VIMNMX with a predicate output of the wrong sense, DESIGN.md "Toolchain note").  The kernels are written to avoid
     the pattern; this keeps it out of the built objects."""
