@@ -47,6 +47,17 @@ int dm_normalize_u16(const float *pred, int B, int H, int W, int invert, int cli
                      float clip_near, uint16_t *depth_out, int32_t *degenerate_flags, void *workspace,
                      size_t workspace_bytes, void *stream);
 
+/* N1, "Outliers" clip:  replaces src/core.py:200-202  (fb, nb = np.percentile(out, [far*100, near*100]); np.clip(out, fb, nb))
+ * followed by the same normalise + convert_to_i16 tail, which numpy evaluates in FLOAT64 here (np.percentile returns
+ * float64 scalars and np.clip promotes the float32 image).  np.percentile's "linear" method reads two order statistics
+ * per percentile: ranks[0..1] / ranks[2..3] are the 0-based ranks (ascending, after the optional sign flip) of the far /
+ * near percentile and gamma_far / gamma_near the float64 interpolation weights; both depend only on H*W and the two
+ * fractions and are computed by the host face with numpy's own expression (core.percentile_plan). */
+size_t dm_normalize_u16_outliers_workspace_bytes(int B);
+int dm_normalize_u16_outliers(const float *pred, int B, int H, int W, int invert, const int64_t ranks[4], double gamma_far,
+                              double gamma_near, uint16_t *depth_out, int32_t *degenerate_flags, void *workspace,
+                              size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * S1-S5 — stereo pair: per-row depth-driven warp + gap fill + packing.
  *            replaces  src/stereoimage_generation.py:13-74 (create_stereoimages),

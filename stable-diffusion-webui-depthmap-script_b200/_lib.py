@@ -57,7 +57,7 @@ _lib = None
 # every symbol include/depthmap_b200.h declares; tests check the built library exports all of them
 EXPORTS = [
     "dm_last_error", "dm_version", "dm_device_name",
-    "dm_normalize_u16_workspace_bytes", "dm_normalize_u16",
+    "dm_normalize_u16_workspace_bytes", "dm_normalize_u16", "dm_normalize_u16_outliers_workspace_bytes", "dm_normalize_u16_outliers",
     "dm_stereo_workspace_bytes", "dm_stereo",
     "dm_normalmap_workspace_bytes", "dm_normalmap",
     "dm_gemm_ex", "dm_conv3x3_ex", "dm_gemm_f16", "dm_conv3x3_f16", "dm_attention_f16", "dm_attention_relpos_f16", "dm_preprocess_patchify",
@@ -83,6 +83,9 @@ def load() -> ctypes.CDLL:
         L.dm_normalize_u16_workspace_bytes.argtypes = [i32]
         L.dm_normalize_u16_workspace_bytes.restype = sz
         L.dm_normalize_u16.argtypes = [vp, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp, sz, vp]
+        L.dm_normalize_u16_outliers_workspace_bytes.argtypes = [i32]
+        L.dm_normalize_u16_outliers_workspace_bytes.restype = sz
+        L.dm_normalize_u16_outliers.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int64), ctypes.c_double, ctypes.c_double, vp, vp, vp, sz, vp]
         L.dm_stereo_workspace_bytes.argtypes = [i32, i32, i32]
         L.dm_stereo_workspace_bytes.restype = sz
         L.dm_stereo.argtypes = [vp, vp, i32, i32, i32, c.POINTER(StereoParams), vp, vp, vp, sz, vp]

@@ -108,24 +108,50 @@ class CoreGenerationFunnelInp:
 # ---------------------------------------------------------------------------------------------------------------------
 # stage functions (batched, device in / device out)
 # ---------------------------------------------------------------------------------------------------------------------
+def percentile_plan(n, fractions):
+    """Where np.percentile(a, [f*100 for f in fractions]) (method "linear", a.size == n) looks: for every fraction the two
+    0-based ranks it reads and the float64 interpolation weight.  Same expressions, same order of operations as numpy's
+    _QuantileMethods['linear'] / _get_indexes / _get_gamma (numpy/lib/_function_base_impl.py) so the weights are bit-identical."""
+    q = np.true_divide(np.asanyarray([f * 100.0 for f in fractions], dtype=np.float64), np.float32(100))
+    if not ((q >= 0).all() and (q <= 1).all()):
+        raise ValueError("Percentiles must be in the range [0, 100]")       # numpy's own message
+    virtual = (n - 1) * q                                  # _QuantileMethods["linear"]["get_virtual_index"]
+    previous = np.floor(virtual).astype(np.intp)
+    nxt = previous + 1
+    above = virtual >= n - 1
+    previous[above] = -1
+    nxt[above] = -1
+    below = virtual < 0
+    previous[below] = 0
+    nxt[below] = 0
+    gamma = np.asanyarray(virtual - previous, dtype=virtual.dtype)
+    return [(int(p) % n, int(x) % n, float(g)) for p, x, g in zip(previous, nxt, gamma)]
+
+
 def normalize_prediction_batch(pred, invert=False, clipdepth=False, clipdepth_mode="Range", far=0.0, near=1.0,
                                return_flags=False):
     """Model prediction float32 CUDA [B,H,W] -> uint16 depth (near = bright).  src/core.py:189-211 + :44-50."""
+    import ctypes
     import torch
     _lib.require_cuda()
     if pred.dtype != torch.float32:
         raise ValueError("prediction must be float32 (the reference's get_raw_prediction returns float32)")
     pred = pred.contiguous()
     B, H, W = pred.shape
-    mode = 0
-    if clipdepth:
-        if clipdepth_mode == "Range":
-            mode = 1
-        else:
-            raise NotImplementedError("CLIPDEPTH_MODE 'Outliers' (np.percentile clip) is a SURVEY §8(f) 'next' row")
     L = _lib.load()
     out = torch.empty((B, H, W), dtype=torch.uint16, device=pred.device)
     flags = torch.empty((B,), dtype=torch.int32, device=pred.device)
+    if clipdepth and clipdepth_mode == "Outliers":      # src/core.py:200-202
+        (p0, n0, g0), (p1, n1, g1) = percentile_plan(H * W, [far, near])
+        ranks = (ctypes.c_int64 * 4)(p0, n0, p1, n1)
+        ws_bytes = L.dm_normalize_u16_outliers_workspace_bytes(B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pred.device)
+        rc = L.dm_normalize_u16_outliers(pred.data_ptr(), B, H, W, 1 if invert else 0, ranks, g0, g1, out.data_ptr(), flags.data_ptr(),
+                                         ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "dm_normalize_u16_outliers")
+        return (out, flags) if return_flags else out
+    # any other mode string: the reference has no else branch (src/core.py:197-202) and leaves the prediction unclipped
+    mode = 1 if (clipdepth and clipdepth_mode == "Range") else 0
     ws_bytes = L.dm_normalize_u16_workspace_bytes(B)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pred.device)
     rc = L.dm_normalize_u16(pred.data_ptr(), B, H, W, 1 if invert else 0, mode, float(far), float(near), out.data_ptr(),

@@ -113,6 +113,136 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// "Outliers" clip (src/core.py:200-202): fb, nb = np.percentile(out, [far*100, near*100]); out = np.clip(out, fb, nb).
+// np.percentile (method "linear") needs, per percentile, the two order statistics around the virtual index and a float64
+// interpolation weight; from there on numpy works in FLOAT64 (percentile returns float64 scalars, so np.clip promotes the
+// float32 image).  The order statistics are found exactly by a 4-pass, 8-bit radix select on the order-preserving integer
+// image of the (sign-applied) values: each pass histograms the digit of the elements that still match each target's
+// prefix, a 4-warp kernel picks the digit that contains the wanted rank.  Ranks and weights are computed by the host
+// face with numpy's own expression (they depend only on H*W and the two fractions).
+// ---------------------------------------------------------------------------------------------------------------------
+struct SelectState {          // per image
+    uint32_t prefix[4];       // key bits decided so far, per target
+    uint32_t rank[4];         // rank still to be found inside the matching subset
+    uint32_t hist[4][256];
+};
+
+__global__ void select_init_kernel(SelectState *st, int B, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    SelectState &s = st[b];
+    if (threadIdx.x < 4) {
+        s.prefix[threadIdx.x] = 0u;
+        s.rank[threadIdx.x] = threadIdx.x == 0 ? r0 : (threadIdx.x == 1 ? r1 : (threadIdx.x == 2 ? r2 : r3));
+    }
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s.hist[0][0])[i] = 0u;
+}
+
+__global__ void __launch_bounds__(256) select_hist_kernel(const float *__restrict__ pred, int64_t n, int invert, int pass, SelectState *st) {
+    __shared__ uint32_t h[4][256];
+    const int b = blockIdx.y;
+    const float *p = pred + (int64_t)b * n;
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&h[0][0])[i] = 0u;
+    const int shift = 24 - 8 * pass;
+    const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    uint32_t pre[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) pre[t] = st[b].prefix[t];
+    __syncthreads();
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nthreads) {
+        const float x = __ldg(p + i);
+        const uint32_t key = f32_to_ordered(invert ? __fmul_rn(x, -1.0f) : x);
+        const uint32_t digit = (key >> shift) & 255u;
+        const uint32_t hi = key & mask;
+        // the two ranks of one percentile (and often all four) share their prefix: count once, add to each matching target
+        if (hi == pre[0]) atomicAdd(&h[0][digit], 1u);
+        if (hi == pre[1]) atomicAdd(&h[1][digit], 1u);
+        if (hi == pre[2]) atomicAdd(&h[2][digit], 1u);
+        if (hi == pre[3]) atomicAdd(&h[3][digit], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
+        const uint32_t v = (&h[0][0])[i];
+        if (v) atomicAdd(&st[b].hist[0][0] + i, v);
+    }
+}
+
+// one warp per target: find the digit whose cumulative count crosses the wanted rank, descend into it
+__global__ void __launch_bounds__(128) select_pick_kernel(SelectState *st, int pass) {
+    const int b = blockIdx.x, t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SelectState &s = st[b];
+    const int shift = 24 - 8 * pass;
+    uint32_t c[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = s.hist[t][lane * 8 + i]; sum += c[i]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t excl = incl - sum;
+    const uint32_t want = s.rank[t];
+    const bool mine = want >= excl && want < incl;      // exactly one lane (the counts add up to the subset size > want)
+    __syncwarp();
+    if (mine) {
+        uint32_t run = excl;
+        int digit = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (want >= run && want < run + c[i]) { digit = lane * 8 + i; break; }
+            run += c[i];
+        }
+        s.prefix[t] |= (uint32_t)digit << shift;
+        s.rank[t] = want - run;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.hist[t][lane * 8 + i] = 0u;
+}
+
+struct OutlierParams {
+    int invert;
+    double gamma_far, gamma_near;     // np.percentile interpolation weights
+};
+
+__global__ void __launch_bounds__(256) quantize_outliers_kernel(const float *__restrict__ pred, int64_t n, const uint32_t *__restrict__ ws,
+                                                                const SelectState *__restrict__ st, OutlierParams op,
+                                                                uint16_t *__restrict__ out, int32_t *degenerate) {
+    const int b = blockIdx.y;
+    const float *p = pred + (int64_t)b * n;
+    uint16_t *o = out + (int64_t)b * n;
+    const float mn = ordered_to_f32(ws[2 * b]), mx = ordered_to_f32(ws[2 * b + 1]);
+    const bool ok = fabs((double)__fsub_rn(mx, mn)) > 2.220446049250313e-16;      // src/core.py:189
+    if (degenerate && blockIdx.x == 0 && threadIdx.x == 0) degenerate[b] = ok ? 0 : 1;
+    // numpy _lerp(a, b, t): diff = b - a in float32; t < 0.5: a + diff * t, else b - diff * (1 - t), in float64
+    auto lerp = [](float a, float bb, double t) {
+        const double diff = (double)__fsub_rn(bb, a);
+        return t >= 0.5 ? __dsub_rn((double)bb, __dmul_rn(diff, __dsub_rn(1.0, t))) : __dadd_rn((double)a, __dmul_rn(diff, t));
+    };
+    const double fb = lerp(ordered_to_f32(st[b].prefix[0]), ordered_to_f32(st[b].prefix[1]), op.gamma_far);
+    const double nb = lerp(ordered_to_f32(st[b].prefix[2]), ordered_to_f32(st[b].prefix[3]), op.gamma_near);
+    const float lo_f = op.invert ? __fmul_rn(mx, -1.0f) : mn, hi_f = op.invert ? __fmul_rn(mn, -1.0f) : mx;
+    // np.clip = minimum(maximum(x, fb), nb); it is monotone, so the extremes of the clipped image are the clipped extremes
+    const double lo = fmin(fmax((double)lo_f, fb), nb), hi = fmin(fmax((double)hi_f, fb), nb);
+    const double den = __dsub_rn(hi, lo);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nthreads) {
+        uint16_t r = 0;
+        if (ok) {
+            const float x = __ldg(p + i);
+            const double v = fmin(fmax((double)(op.invert ? __fmul_rn(x, -1.0f) : x), fb), nb);
+            double q = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(v, lo), den), 65536.0), 0.0001);
+            q = fmin(fmax(q, 0.0), 65535.9);
+            r = (q == q) ? (uint16_t)(int)q : (uint16_t)0;        // 0/0 when the clip collapses the range: numpy's NaN -> 0
+        }
+        o[i] = r;
+    }
+}
+
 }  // namespace dm
 
 extern "C" __attribute__((visibility("default"))) size_t dm_normalize_u16_workspace_bytes(int B) { return dm::align_up((size_t)(B > 0 ? B : 1) * 2 * sizeof(uint32_t), 256); }
@@ -140,5 +270,49 @@ extern "C" __attribute__((visibility("default"))) int dm_normalize_u16(const flo
     QuantParams qp{invert ? 1 : 0, clip_mode, clip_far, clip_near};
     quantize_kernel<<<grid, 256, 0, stream>>>(pred, n, ws, qp, depth_out, degenerate_flags, vec_ok);
     DM_LAUNCH_CHECK("quantize_kernel");
+    return DM_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t dm_normalize_u16_outliers_workspace_bytes(int B) {
+    const size_t b = (size_t)(B > 0 ? B : 1);
+    return dm::align_up(b * 2 * sizeof(uint32_t), 256) + dm::align_up(b * sizeof(dm::SelectState), 256);
+}
+
+extern "C" __attribute__((visibility("default"))) int dm_normalize_u16_outliers(const float *pred, int B, int H, int W, int invert, const int64_t ranks[4],
+                                         double gamma_far, double gamma_near, uint16_t *depth_out, int32_t *degenerate_flags,
+                                         void *workspace, size_t workspace_bytes, void *stream_) {
+    using namespace dm;
+    if (!pred || !depth_out || !ranks || B <= 0 || H <= 0 || W <= 0) { set_error("dm_normalize_u16_outliers: bad arguments"); return DM_E_INVALID; }
+    const int64_t n = (int64_t)H * W;
+    for (int i = 0; i < 4; ++i)
+        if (ranks[i] < 0 || ranks[i] >= n || n >= (1ll << 32)) { set_error("dm_normalize_u16_outliers: rank %d out of range", i); return DM_E_INVALID; }
+    if (!workspace || workspace_bytes < dm_normalize_u16_outliers_workspace_bytes(B)) { set_error("dm_normalize_u16_outliers: workspace too small"); return DM_E_WORKSPACE; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    uint32_t *ws = (uint32_t *)workspace;
+    SelectState *st = (SelectState *)((uint8_t *)workspace + align_up((size_t)B * 2 * sizeof(uint32_t), 256));
+    const int vec_ok = (n % 4 == 0) && (((uintptr_t)pred) % 16 == 0);
+    minmax_init_kernel<<<(B + 255) / 256, 256, 0, stream>>>(ws, B);
+    DM_LAUNCH_CHECK("minmax_init_kernel");
+    int64_t work = vec_ok ? n / 4 : n;
+    int bx = (int)((work + 256 * 4 - 1) / (256 * 4));
+    if (bx < 1) bx = 1;
+    if (bx > 148 * 8) bx = 148 * 8;
+    dim3 grid(bx, B);
+    minmax_f32_kernel<<<grid, 256, 0, stream>>>(pred, n, ws, vec_ok);
+    DM_LAUNCH_CHECK("minmax_f32_kernel");
+    select_init_kernel<<<B, 256, 0, stream>>>(st, B, (uint32_t)ranks[0], (uint32_t)ranks[1], (uint32_t)ranks[2], (uint32_t)ranks[3]);
+    DM_LAUNCH_CHECK("select_init_kernel");
+    int sx = (int)((n + 256 * 16 - 1) / (256 * 16));
+    if (sx < 1) sx = 1;
+    if (sx > 148 * 4) sx = 148 * 4;
+    for (int pass = 0; pass < 4; ++pass) {
+        select_hist_kernel<<<dim3(sx, B), 256, 0, stream>>>(pred, n, invert ? 1 : 0, pass, st);
+        DM_LAUNCH_CHECK("select_hist_kernel");
+        select_pick_kernel<<<B, 128, 0, stream>>>(st, pass);
+        DM_LAUNCH_CHECK("select_pick_kernel");
+    }
+    OutlierParams op{invert ? 1 : 0, gamma_far, gamma_near};
+    quantize_outliers_kernel<<<grid, 256, 0, stream>>>(pred, n, ws, st, op, depth_out, degenerate_flags);
+    DM_LAUNCH_CHECK("quantize_outliers_kernel");
     return DM_OK;
 }

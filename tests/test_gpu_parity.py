@@ -167,6 +167,29 @@ def test_normalize_batch_vs_oracle(cuda_device, hw):
             assert int(flags[-1]) == 1
 
 
+@pytest.mark.parametrize("hw", [(48, 64), (37, 518), (1, 1), (7, 3), (512, 512)])
+def test_normalize_outliers_clip_vs_oracle(cuda_device, hw):
+    """CLIPDEPTH_MODE 'Outliers' (src/core.py:200-202): np.percentile bounds from an exact radix select, float64 tail."""
+    import warnings
+    import torch
+    from depthmap_b200.core import normalize_prediction_batch
+    from oracle import normalmap as onm
+    h, w = hw
+    rng = np.random.default_rng(7 * h + w)
+    preds = [(rng.standard_normal((h, w)) * 10 ** rng.uniform(-4, 4) + rng.uniform(-3, 3)).astype(np.float32) for _ in range(3)]
+    preds.append(np.round(rng.standard_normal((h, w)) * 3).astype(np.float32))   # heavy ties (and +-0)
+    preds.append(np.full((h, w), -2.5, np.float32))                              # degenerate -> black
+    t = torch.from_numpy(np.stack(preds)).to(cuda_device)
+    for inv in (False, True):
+        for (far, near) in [(0.05, 0.95), (0.0, 1.0), (0.123456, 0.5), (0.5, 0.5), (0.999, 1.0)]:
+            got = normalize_prediction_batch(t, inv, True, "Outliers", far, near).cpu().numpy()
+            for b in range(len(preds)):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")          # the collapsed-range case divides 0 by 0 in numpy
+                    want = onm.normalize_to_u16(preds[b], inv, True, "Outliers", far, near)
+                assert np.array_equal(got[b], want), (hw, b, inv, far, near, int((got[b] != want).sum()))
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # BASELINE-size properties (no oracle at these sizes beyond one spot row block)
 # ----------------------------------------------------------------------------------------------------------------
