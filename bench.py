@@ -316,7 +316,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # a collective that cannot complete (a sick link, a rank that died) raises after 5 minutes instead of hanging the job
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=5))
 
     import __graft_entry__ as ge
     if rank == 0:
