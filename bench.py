@@ -153,7 +153,9 @@ class Stereo2048:
         alg = 11.0 * self.H * self.W * self.B  # 3 (RGB) + 2 (depth) in, 6 (two eyes) out per pixel
         achieved = alg / (kernel_ms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": "stereo_row_kernel (+ u16 min/max pre-pass)", "achieved": achieved,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                # dram read + write of the row kernel for this batch (profiles/r01_ncu_stereo2048.txt): no re-reads
+                "traffic": 692.5e6 if (self.B == 16 and self.fill == "polylines_sharp") else None, "traffic_unit": "bytes/launch (ncu --set full)",
                 "peak_source": peaks["source"], "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
                 "note": "exact-fp64 polylines is FP64/latency bound, not HBM bound; see DESIGN.md"}
 

@@ -162,7 +162,10 @@ class DepthBeit512:
         achieved = self.fc1_flops / (kernel_ms * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": "gemm_tcgen05_2sm_kernel (cta_group::2, 256x256 tile pair; block-0 MLP fc1: M=B*1025, N=4096, K=1024, GELU epilogue)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": None, "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "algorithmic_flops_per_launch": self.fc1_flops,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch (B = 32), profiles/r01_ncu_gemm_2sm_fc1.txt;
+                # algorithmic: A 67 MB + W 8 MB in, C 269 MB out
+                "traffic": 316.4e6 if self.B == 32 else None, "traffic_unit": "bytes/launch (ncu --set full)",
+                "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "algorithmic_flops_per_launch": self.fc1_flops,
                 "kernel_ms": kernel_ms}
 
     def extra(self, ms_step, peaks):
