@@ -56,3 +56,53 @@ def test_normalmap_oracle_equals_reference(ref):
             a = np.asarray(rn.create_normalmap(dep, pb, sb, qb, inv))
             b = onm.create_normalmap(dep, pb, sb, qb, inv, return_array=True)
             assert np.array_equal(a, b), (seed, pb, sb, qb, inv)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# D7 (round-2 row): the ZoeDepth-NK metric head oracle against the reference module built around a stub core
+# ---------------------------------------------------------------------------------------------------------------------
+def _zoedepth_reference_head(seed, base_hw):
+    import torch
+    import torch.nn as nn
+    ref_loader.bootstrap()
+    from dzoedepth.models.zoedepth_nk.zoedepth_nk_v1 import ZoeDepthNK
+    from oracle import zoedepth as ozd
+    g = torch.Generator().manual_seed(seed)
+    h, w = base_hw
+    shapes = [(32, 16 * h, 16 * w), (256, h, w), (256, 2 * h, 2 * w), (256, 4 * h, 4 * w), (256, 8 * h, 8 * w), (256, 16 * h, 16 * w)]
+    feats = [torch.randn(2, c, hh, ww, generator=g) * 0.7 for c, hh, ww in shapes]
+    feats[0] = feats[0].abs()                      # out_conv is a post-ReLU activation in the core
+
+    class StubCore(nn.Module):                     # hands the head fixed activations (MidasCore.forward, midas.py:258-276)
+        output_channels = (256, 256, 256, 256, 256)
+
+        def forward(self, x, denorm=False, return_rel_depth=False):
+            return torch.zeros(x.shape[0], x.shape[2], x.shape[3]), [f.clone() for f in feats]
+
+    cfg = {k: ozd.CONFIG[k] for k in ("bin_embedding_dim", "n_attractors", "attractor_alpha", "attractor_gamma", "min_temp", "max_temp")}
+
+    class AttrDict(dict):                          # the reference reads its config entries as attributes (EasyDict)
+        __getattr__ = dict.__getitem__
+
+    model = ZoeDepthNK(StubCore(), bin_conf=[AttrDict(c) for c in ozd.CONFIG["bin_conf"]], bin_centers_type="softplus", attractor_kind="mean",
+                       attractor_type="inv", memory_efficient=True, **cfg).eval()
+    with torch.no_grad():                          # seeded weights with enough spread to exercise every branch
+        for name, p in model.named_parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.05 if p.ndim > 1 else 0.02))
+            if name.endswith("norm1.weight") or name.endswith("norm2.weight"):
+                p.add_(1.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items() if not k.startswith("core.")}
+    return model, feats, sd
+
+
+@pytest.mark.parametrize("seed,base_hw", [(0, (3, 4)), (1, (4, 3)), (2, (2, 2))])
+def test_zoedepth_head_oracle_equals_reference(seed, base_hw):
+    import torch
+    from oracle import zoedepth as ozd
+    model, feats, sd = _zoedepth_reference_head(seed, base_hw)
+    with torch.no_grad():
+        want = model(torch.zeros(2, 3, feats[0].shape[2], feats[0].shape[3]))
+        got_depth, got_logits, name = ozd.metric_head(feats, sd)
+    assert torch.equal(got_logits, want["domain_logits"]) or (got_logits - want["domain_logits"]).abs().max() < 1e-5
+    err = (got_depth - want["metric_depth"]).abs().max().item()
+    assert err <= 1e-5 * want["metric_depth"].abs().max().item(), (name, err)
