@@ -151,8 +151,9 @@ def _fusion(sd, key, x0, x1=None, size=None):
     return _conv(sd, key + '.out_conv', output)
 
 
-def forward(sd, x, name):
-    """DPTDepthModel.forward: x [B,3,H,W] -> [B,H,W]."""
+def forward(sd, x, name, return_features=False):
+    """DPTDepthModel.forward: x [B,3,H,W] -> [B,H,W].  With return_features also the six activations ZoeDepth's MidasCore
+    hooks (dzoedepth/models/base_models/midas.py:298-316): output_conv child 3 (the 32-channel ReLU), layer4_rn, refinenet4..1."""
     cfg = CONFIGS[name]
     B, _, H, W = x.shape
     gh, gw = H // 16, W // 16
@@ -183,7 +184,10 @@ def forward(sd, x, name):
     o = _conv(sd, 'scratch.output_conv.0', p1, padding=1)
     o = F.interpolate(o, scale_factor=2, mode="bilinear", align_corners=True)
     o = F.relu(_conv(sd, 'scratch.output_conv.2', o, padding=1))
+    feats = [o, l4, p4, p3, p2, p1]
     o = F.relu(_conv(sd, 'scratch.output_conv.4', o))
+    if return_features:
+        return o.squeeze(1), feats
     return o.squeeze(1)
 
 

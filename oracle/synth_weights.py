@@ -138,3 +138,54 @@ def make_beit_dpt_state_dict(name='beit_tiny', seed=0, dtype=torch.float32):
     sd['scratch.output_conv.4.weight'] = rn(1, 32, 1, 1, std=0.08, mean=0.05)
     sd['scratch.output_conv.4.bias'] = torch.full((1,), 0.5, dtype=dtype)
     return sd
+
+
+def make_zoedepth_head_state_dict(feat_ch=256, out_conv_ch=32, seed=0, dtype=torch.float32):
+    """Seeded ZoeDepth-NK metric-head weights in the checkpoint layout of dzoedepth/models/zoedepth_nk/zoedepth_nk_v1.py
+    (keys as `ZoeDepthNK.state_dict()` minus "core."): 64 bins, 128-d bin embedding, 16 attractors per level (the count the
+    reference really instantiates, see oracle/zoedepth.py), 4-layer / 4-head / 1024-ffn router."""
+    g = torch.Generator().manual_seed(seed)
+
+    def w(*shape, s=0.05):
+        return (torch.randn(*shape, generator=g) * s).to(dtype)
+
+    sd = {}
+
+    def conv(key, cout, cin):
+        sd[key + ".weight"] = w(cout, cin, 1, 1)
+        sd[key + ".bias"] = w(cout, s=0.02)
+
+    def lin(key, cout, cin):
+        sd[key + ".weight"] = w(cout, cin)
+        sd[key + ".bias"] = w(cout, s=0.02)
+
+    E, emb, nb = 128, 128, 64
+    conv("conv2", feat_ch, feat_ch)
+    conv("patch_transformer.embedding_convPxP", E, feat_ch)
+    for i in range(4):
+        p = f"patch_transformer.transformer_encoder.layers.{i}"
+        sd[p + ".self_attn.in_proj_weight"] = w(3 * E, E)
+        sd[p + ".self_attn.in_proj_bias"] = w(3 * E, s=0.02)
+        lin(p + ".self_attn.out_proj", E, E)
+        lin(p + ".linear1", 1024, E)
+        lin(p + ".linear2", E, 1024)
+        for n in ("norm1", "norm2"):
+            sd[p + f".{n}.weight"] = 1.0 + w(E, s=0.02)
+            sd[p + f".{n}.bias"] = w(E, s=0.02)
+    lin("mlp_classifier.0", 128, E)
+    lin("mlp_classifier.2", 2, 128)
+    for name in ("nyu", "kitti"):
+        conv(f"seed_bin_regressors.{name}._net.0", emb // 2, feat_ch)
+        conv(f"seed_bin_regressors.{name}._net.2", nb, emb // 2)
+        for i in range(4):
+            conv(f"attractors.{name}.{i}._net.0", emb, emb)
+            conv(f"attractors.{name}.{i}._net.2", 16, emb)
+        bott = (out_conv_ch + emb) // 4
+        conv(f"conditional_log_binomial.{name}.mlp.0", bott, out_conv_ch + emb)
+        conv(f"conditional_log_binomial.{name}.mlp.2", 4, bott)
+    conv("seed_projector._net.0", emb // 2, feat_ch)
+    conv("seed_projector._net.2", emb, emb // 2)
+    for i in range(4):
+        conv(f"projectors.{i}._net.0", emb // 2, feat_ch)
+        conv(f"projectors.{i}._net.2", emb, emb // 2)
+    return sd

@@ -141,3 +141,73 @@ def metric_head(features, sd):
     b_emb = F.interpolate(b_emb, outconv.shape[-2:], mode="bilinear", align_corners=True)
     probs = _conditional_log_binomial(outconv, b_emb, sd, f"conditional_log_binomial.{name}", conf["n_bins"])
     return torch.sum(probs * b_centers, dim=1, keepdim=True), logits, name
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# test-time augmentation wrapper: dzoedepth/models/depth_model.py:57-129 (DepthModel.infer = flip aug over pad aug)
+# ---------------------------------------------------------------------------------------------------------------------
+def infer_with_pad_aug(model_fn, x, pad_input=True, fh=3.0, fw=3.0):
+    """model_fn(x [B,3,H,W]) -> metric depth [B,1,h,w].  Reflect-pads by int(sqrt(H/2)*fh) rows / int(sqrt(W/2)*fw) columns,
+    runs the model, brings the output to the padded input size (bicubic, align_corners=False) and crops the padding away."""
+    import numpy as np
+    assert x.dim() == 4 and x.shape[1] == 3
+    pad_h = pad_w = 0
+    if pad_input:
+        pad_h = int(np.sqrt(x.shape[2] / 2) * fh)
+        pad_w = int(np.sqrt(x.shape[3] / 2) * fw)
+        padding = [pad_w, pad_w]
+        if pad_h > 0:
+            padding += [pad_h, pad_h]
+        x = F.pad(x, padding, mode="reflect")
+    out = model_fn(x)
+    if out.shape[-2:] != x.shape[-2:]:
+        out = F.interpolate(out, size=(x.shape[2], x.shape[3]), mode="bicubic", align_corners=False)
+    if pad_input:
+        if pad_h > 0:
+            out = out[:, :, pad_h:-pad_h, :]
+        if pad_w > 0:
+            out = out[:, :, :, pad_w:-pad_w]
+    return out
+
+
+def infer(model_fn, x, pad_input=True, with_flip_aug=True):
+    """DepthModel.infer: mean of the prediction and the un-flipped prediction of the horizontally flipped input."""
+    out = infer_with_pad_aug(model_fn, x, pad_input)
+    if not with_flip_aug:
+        return out
+    out_flip = infer_with_pad_aug(model_fn, torch.flip(x, dims=[3]), pad_input)
+    return (out + torch.flip(out_flip, dims=[3])) / 2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole D7 path: estimatezoedepth (src/depthmap_generation.py:443-452) -> DepthModel.infer_pil -> MidasCore -> head.
+# The DPT-BEiT-L-384 core is oracle/beit_dpt.py (parity unpinned: timm is absent, see its header); everything after the
+# core's activations is pinned above.
+# ---------------------------------------------------------------------------------------------------------------------
+def prep_for_midas(x, net_w, net_h):
+    """PrepForMidas (midas.py:175-186) as ZoeDepth-NK configures it: keep_aspect_ratio (force_keep_ar), multiple of 32,
+    resize_method "minimal", bilinear align_corners=True, then (x - 0.5) / 0.5."""
+    from oracle import beit_dpt
+    w, h = beit_dpt.get_size_minimal(x.shape[3], x.shape[2], net_w, net_h, 32)
+    x = F.interpolate(x, (int(h), int(w)), mode="bilinear", align_corners=True)
+    return (x - 0.5) / 0.5
+
+
+@torch.no_grad()
+def get_raw_prediction(rgb_uint8, sd, net_w=512, net_h=384, core_name="beitl16_384"):
+    """ModelHolder.get_raw_prediction for model type 9 (zoedepth_nk): (float32 metric depth [H,W], invert=True).
+    sd: ZoeDepth checkpoint layout — MiDaS weights under "core.core.", head weights at the top level."""
+    import numpy as np
+    from oracle import beit_dpt
+    core_sd = {k[len("core.core."):]: v for k, v in sd.items() if k.startswith("core.core.")}
+    head_sd = {k: v for k, v in sd.items() if not k.startswith("core.")}
+
+    def model_fn(x):
+        xin = prep_for_midas(x, net_w, net_h)
+        _, feats = beit_dpt.forward(core_sd, xin, core_name, return_features=True)
+        return metric_head(feats, head_sd)[0]
+
+    img = np.asarray(rgb_uint8)
+    x = torch.from_numpy(np.ascontiguousarray(img)).permute(2, 0, 1).float().div(255.0).unsqueeze(0)      # transforms.ToTensor
+    out = infer(model_fn, x, pad_input=True, with_flip_aug=True)
+    return out.squeeze().cpu().numpy(), True

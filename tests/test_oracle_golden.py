@@ -62,3 +62,23 @@ def test_oracle_stereo_api_edges():
         ost.create_stereoimages(img, dep[:3], 2.5)
     out = ost.create_stereoimages(img, dep, 2.5, modes="left-right")
     assert out[0].size == (12, 4)
+
+
+def test_zoedepth_oracle_path_runs_and_is_flip_symmetric():
+    """D7 oracle end to end on the tiny structural configuration (beit_tiny core + metric head + pad / flip TTA): shape, range
+    and the exact flip symmetry DepthModel.infer has by construction.  (The head and the TTA wrapper are pinned to the
+    reference module in tests/test_oracle_pin.py; the BEiT core is parity-unpinned, see oracle/beit_dpt.py.)"""
+    import torch
+    from oracle import synth_weights, zoedepth
+    from synth import synth_rgb
+    core = synth_weights.make_beit_dpt_state_dict("beit_tiny", seed=3)
+    feat = core["scratch.layer4_rn.weight"].shape[0]
+    outc = core["scratch.output_conv.2.weight"].shape[0]
+    sd = {("core.core." + k): v for k, v in core.items()}
+    sd.update(synth_weights.make_zoedepth_head_state_dict(feat, outc, seed=4))
+    rgb = synth_rgb(48, 64, 1)
+    d, invert = zoedepth.get_raw_prediction(rgb, sd, net_w=64, net_h=64, core_name="beit_tiny")
+    assert invert is True and d.shape == (48, 64) and d.dtype == np.float32
+    assert np.isfinite(d).all() and (d > 0).all()
+    d2, _ = zoedepth.get_raw_prediction(np.ascontiguousarray(rgb[:, ::-1]), sd, net_w=64, net_h=64, core_name="beit_tiny")
+    assert np.allclose(d2[:, ::-1], d, rtol=0, atol=1e-6 * float(d.max()))

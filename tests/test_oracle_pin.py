@@ -106,3 +106,18 @@ def test_zoedepth_head_oracle_equals_reference(seed, base_hw):
     assert torch.equal(got_logits, want["domain_logits"]) or (got_logits - want["domain_logits"]).abs().max() < 1e-5
     err = (got_depth - want["metric_depth"]).abs().max().item()
     assert err <= 1e-5 * want["metric_depth"].abs().max().item(), (name, err)
+
+
+@pytest.mark.parametrize("pad,flip", [(True, True), (True, False), (False, True)])
+def test_zoedepth_tta_wrapper_equals_reference(pad, flip):
+    """DepthModel.infer (pad + flip augmentation) around the same head: the stub core ignores its input, so this pins the
+    padding arithmetic, the bicubic resize back to the padded size, the crop and the flip average."""
+    import torch
+    from oracle import zoedepth as ozd
+    model, feats, sd = _zoedepth_reference_head(3, (2, 3))
+    x = torch.rand(2, 3, 40, 56, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        want = model.infer(x, pad_input=pad, with_flip_aug=flip)
+        got = ozd.infer(lambda t: ozd.metric_head(feats, sd)[0], x, pad_input=pad, with_flip_aug=flip)
+    assert got.shape == want.shape == (2, 1, 40, 56)
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
