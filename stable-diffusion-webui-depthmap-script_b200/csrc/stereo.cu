@@ -37,6 +37,7 @@ struct StereoArgs {
     double div_px[2], sep_px[2];
     int eye_mode[2];
     int fill, pack, red_eye, depth_kind;
+    double *dbg;    // debug dump (tests only): row 0 / image 0 / first warped eye -> [n, pm[n], order[n], off[W+2]]
     uint8_t *out[2];
     int64_t row_stride[2], img_stride[2];
 };
@@ -176,7 +177,7 @@ __device__ __forceinline__ double vertex_x(int t, int n, int W, const NdSrc &nds
 }
 
 template <bool SHARP>
-__device__ void polylines_eye(const RowSmem &sm, const NdSrc &nds, int W, double div_px, double sep_px, uint32_t dst_off) {
+__device__ void polylines_eye(const RowSmem &sm, const NdSrc &nds, int W, double div_px, double sep_px, uint32_t dst_off, double *dbg) {
     const int tid = threadIdx.x, T_ = blockDim.x;
     const int n = SHARP ? 2 * W + 2 : W + 2;
     const bool fwd = !(div_px < 0.0);
@@ -242,6 +243,11 @@ __device__ void polylines_eye(const RowSmem &sm, const NdSrc &nds, int W, double
         }
     }
     __syncthreads();
+    if (dbg && tid == 0) {
+        dbg[0] = n;
+        for (int t = 0; t < n; ++t) { dbg[1 + t] = pm[t]; dbg[1 + n + t] = order[t]; dbg[1 + 2 * n + t] = xs[t]; }
+        for (int b = 0; b < W + 2; ++b) dbg[1 + 3 * n + b] = off[b + 1];
+    }
     // 4. rasterise: one output pixel per thread iteration (:228-281)
     for (int col = tid; col < W; col += T_) {
         double c0 = 0.5, c1 = 0.5, c2 = 0.5;
@@ -474,9 +480,9 @@ __global__ void __launch_bounds__(256, POLY ? 2 : 4) stereo_row_kernel(StereoArg
             __syncthreads();
         } else if (POLY) {
             if (a.fill == DM_FILL_POLYLINES_SHARP)
-                polylines_eye<true>(sm, nds, W, a.div_px[e], a.sep_px[e], dst_off);
+                polylines_eye<true>(sm, nds, W, a.div_px[e], a.sep_px[e], dst_off, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
             else
-                polylines_eye<false>(sm, nds, W, a.div_px[e], a.sep_px[e], dst_off);
+                polylines_eye<false>(sm, nds, W, a.div_px[e], a.sep_px[e], dst_off, (y == 0 && b == 0 && e == 0) ? a.dbg : nullptr);
         } else {
             naive_eye(sm, nds, W, a.div_px[e], a.sep_px[e], a.fill, dst_off);
         }
@@ -549,6 +555,9 @@ static size_t stereo_smem_bytes(int W, int fill, int depth_kind) {
 
 }  // namespace dm
 
+static double *g_stereo_dbg = nullptr;
+// bring-up hook, not part of the C-ABI (hidden symbol): dumps the sorted vertex arrays of row 0 / image 0 / first warped eye
+extern "C" void dm_stereo_set_debug_buffer(double *dev_buf) { g_stereo_dbg = dev_buf; }
 
 extern "C" __attribute__((visibility("default"))) size_t dm_stereo_workspace_bytes(int B, int H, int W) {
     (void)H; (void)W;
@@ -601,6 +610,7 @@ extern "C" __attribute__((visibility("default"))) int dm_stereo(const uint8_t *r
     }
     a.fill = p->fill; a.pack = p->pack; a.red_eye = p->anaglyph_red_eye ? 1 : 0; a.depth_kind = p->depth_kind;
     a.out[0] = out0; a.out[1] = out1;
+    a.dbg = g_stereo_dbg;
     const int pow_kind = p->exponent == 1.0 ? 0 : (p->exponent == 2.0 ? 1 : 2);
     const int threads = W <= 256 ? 128 : 256;
     if (poly) stereo_row_kernel<true><<<dim3(H, B), threads, smem, stream>>>(a, pow_kind);
