@@ -121,3 +121,21 @@ def test_zoedepth_tta_wrapper_equals_reference(pad, flip):
         got = ozd.infer(lambda t: ozd.metric_head(feats, sd)[0], x, pad_input=pad, with_flip_aug=flip)
     assert got.shape == want.shape == (2, 1, 40, 56)
     assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("smoothening", ["none", "experimental", "something-else"])
+def test_video_normalisation_equals_reference(smoothening):
+    """§8(f) rank 1 groundwork: cross-frame normalisation of video mode (src/video_mode.py:103-128)."""
+    ref_loader.bootstrap()
+    try:
+        from src import video_mode
+    except Exception as e:          # optional host dependencies of the video writer
+        pytest.skip(f"src.video_mode not importable here: {e}")
+    from oracle import video as ovid
+    rng = np.random.default_rng(11)
+    frames = [(rng.standard_normal((24, 32)) * (1 + 0.3 * i) + 0.1 * i).astype(np.float32) for i in range(7)]
+    want = video_mode.process_predicitons([f.copy() for f in frames], smoothening)
+    got = ovid.process_predictions([f.copy() for f in frames], smoothening)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.dtype == w.dtype and np.array_equal(g, w)
