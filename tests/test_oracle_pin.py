@@ -197,3 +197,31 @@ def test_leres_estimate_equals_reference(leres_reference):
     got, invert = leres.get_raw_prediction(img, sd, 64, 96)
     assert invert is True and got.shape == want.shape == (70, 90)
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_pix2pix_unet_oracle_equals_reference():
+    """D9 groundwork: the BOOST merge network (10-level U-Net, norm 'none') and its input preparation."""
+    import torch
+    ref_loader.bootstrap()
+    from pix2pix.models import networks
+    from oracle import pix2pix as op2p
+    net = networks.define_G(2, 1, 64, 'unet_1024', 'none', False, 'normal', 0.02, []).eval()
+    g = torch.Generator().manual_seed(31)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if p.ndim == 4:
+                p.copy_(torch.randn(p.shape, generator=g) * (1.6 / (p.shape[1] * 16) ** 0.5))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    rng = np.random.default_rng(5)
+    outer = rng.standard_normal((1024, 1024)).astype(np.float32)
+    inner = (outer * 0.5 + rng.standard_normal((1024, 1024)).astype(np.float32)).astype(np.float32)
+    x = op2p.merge_input(outer, inner)
+    assert x.shape == (1, 2, 1024, 1024) and float(x.min()) == -1.0 and float(x.max()) == 1.0
+    with torch.no_grad():
+        want = net(x.clone())
+        got = op2p.unet(sd, x.clone())
+    assert got.shape == want.shape == (1, 1, 1024, 1024)
+    assert float(want.abs().max()) > 1e-3          # the seeded weights keep a signal through the 20 layers
+    assert (got - want).abs().max().item() <= 1e-5
