@@ -225,3 +225,39 @@ def test_pix2pix_unet_oracle_equals_reference():
     assert got.shape == want.shape == (1, 1, 1024, 1024)
     assert float(want.abs().max()) > 1e-3          # the seeded weights keep a signal through the 20 layers
     assert (got - want).abs().max().item() <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Depth-Anything-V2 (D5 / D6): the oracle restatement against the reference's own DepthAnythingV2 module
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("encoder,hw,net", [("vits", (70, 98), 70), ("vits", (84, 56), 56), ("vitb", (70, 70), 70)])
+def test_dav2_oracle_equals_reference(encoder, hw, net):
+    """ddepth_anything_v2/depth_anything_v2/dpt.py:176-221 + src/depthmap_generation.py:375-403,548-559: strict
+    state_dict load of the synthetic weights into the reference module, then the reference's own pre-processing /
+    forward / final resize against oracle.dav2.get_raw_prediction on the same uint8 image -> identical floats."""
+    import cv2
+    import torch
+    import torch.nn.functional as F
+    from oracle import dav2 as odav2
+    from oracle import synth_weights
+    cls = ref_loader.dav2_class()
+    sd = synth_weights.make_dav2_state_dict(encoder, seed=1)
+    cfg = odav2.CONFIGS[encoder]
+    model = cls(encoder=encoder, features=cfg['features'], out_channels=cfg['out_channels']).eval()
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    rgb = synth_rgb(hw[0], hw[1], 3)
+    # the reference's call chain, verbatim: get_raw_prediction (:381) -> estimatedepthanything_v2 (:548-559)
+    img = cv2.cvtColor(np.asarray(rgb), cv2.COLOR_BGR2RGB) / 255.0
+    with torch.no_grad():
+        image = cv2.cvtColor((img * 255.1).astype('uint8'), cv2.COLOR_BGR2RGB)
+        image, (h, w) = model.image2tensor(image, net)
+        image = image.to('cpu')
+        depth = model.forward(image)
+        depth = F.interpolate(depth[:, None], (h, w), mode="bilinear", align_corners=True)[0, 0]
+    want = depth.cpu().numpy()
+    got, invert = odav2.get_raw_prediction(rgb, sd, encoder, net)
+    assert invert is False
+    assert want.max() - want.min() > 0.1          # a non-degenerate map (default init would be identically zero)
+    assert got.shape == want.shape == tuple(hw)
+    assert float(np.abs(got - want).max()) <= 1e-6 * float(np.abs(want).max()), float(np.abs(got - want).max())
