@@ -173,6 +173,14 @@ def convert_to_i16(arr):
     return out.to(torch.int32).cpu().numpy().astype("uint16")
 
 
+def convert_to_i16_batch(t):
+    """float64 CUDA tensor in [0, 1) -> uint16 CUDA tensor; the arithmetic of src/core.py:44-50 in float64 (what numpy
+    does for the float64 custom depth maps of src/core.py:146-174)."""
+    import torch
+    q = torch.clamp(t.to(torch.float64) * 65536 + 0.0001, 0, 65536 - 0.1).to(torch.int32)
+    return q.to(torch.int16).view(torch.uint16)  # values < 65536: the int16 wrap is the uint16 bit pattern
+
+
 def convert_i16_to_rgb(image, like):
     """reference: src/core.py:52-58 (host-side formatting helper for OUTPUT_DEPTH_COMBINE)."""
     output = np.zeros_like(like)
@@ -217,8 +225,66 @@ def _custom_depth_to_unit(dp, image):
     return out
 
 
-def core_generation_funnel(outpath, inputimages, inputdepthmaps, inputnames, inp, ops=None):
+def max_batch_for(width, height):
+    """Upper bound on the images of one funnel batch (video mode hands every frame of a clip to one call).
+    Bounded by pixel count so that the per-batch activation buffers stay at a few GB whatever the clip length;
+    DEPTHMAP_B200_MAX_BATCH overrides."""
+    import os
+    env = os.environ.get("DEPTHMAP_B200_MAX_BATCH")
+    if env:
+        return max(1, int(env))
+    return int(max(1, min(64, (1 << 24) // max(1, int(width) * int(height)))))
+
+
+def _process_chunk(holder, inp, dev, images, depthmaps, idxs):
+    """One batch of equally sized images through every requested stage on the device; returns per-image host results."""
     import torch
+    custom = depthmaps[idxs[0]] is not None
+    rgbs = [np.asarray(images[i].convert('RGB') if images[i].mode != 'RGB' else images[i]) for i in idxs]
+    rgb_t = torch.from_numpy(np.stack(rgbs)).to(dev, non_blocking=True)
+    w, h = images[idxs[0]].width, images[idxs[0]].height
+    preds = flags = None
+    invert = False
+    if custom:
+        outs = [_custom_depth_to_unit(depthmaps[i], images[i]) for i in idxs]
+        depth_u16 = convert_to_i16_batch(torch.from_numpy(np.stack(outs)).to(dev))
+    else:
+        if inp[go.NET_SIZE_MATCH]:
+            net_width, net_height = (w + 31) // 32 * 32, (h + 31) // 32 * 32
+        else:
+            net_width, net_height = inp[go.NET_WIDTH], inp[go.NET_HEIGHT]
+        preds, invert = holder.get_raw_prediction_batch(rgb_t, net_width, net_height)
+        depth_u16, flags = normalize_prediction_batch(
+            preds, invert, inp[go.CLIPDEPTH], inp[go.CLIPDEPTH_MODE], inp[go.CLIPDEPTH_FAR],
+            inp[go.CLIPDEPTH_NEAR], return_flags=True)
+    stereo = None
+    if inp[go.GEN_STEREO]:
+        stereo = create_stereoimages_batch(
+            rgb_t, depth_u16, inp[go.STEREO_DIVERGENCE], inp[go.STEREO_SEPARATION], inp[go.STEREO_MODES],
+            inp[go.STEREO_BALANCE], inp[go.STEREO_OFFSET_EXPONENT], inp[go.STEREO_FILL_ALGO])
+    normal = None
+    if inp[go.GEN_NORMALMAP]:
+        normal = create_normalmap_batch(
+            depth_u16,
+            inp[go.NORMALMAP_PRE_BLUR_KERNEL] if inp[go.NORMALMAP_PRE_BLUR] else None,
+            inp[go.NORMALMAP_SOBEL_KERNEL] if inp[go.NORMALMAP_SOBEL] else None,
+            inp[go.NORMALMAP_POST_BLUR_KERNEL] if inp[go.NORMALMAP_POST_BLUR] else None,
+            inp[go.NORMALMAP_INVERT])
+    # one device -> host transfer per tensor per batch
+    depth_h = depth_u16.cpu().numpy()
+    preds_h = preds.cpu().numpy() if preds is not None else None
+    flags_h = flags.cpu().numpy() if flags is not None else None
+    stereo_h = [s.cpu().numpy() for s in stereo] if stereo is not None else None
+    normal_h = normal.cpu().numpy() if normal is not None else None
+    out = []
+    for j in range(len(idxs)):
+        out.append((rgbs[j], depth_h[j], None if preds_h is None else (preds_h[j], invert, int(flags_h[j])),
+                    None if stereo_h is None else [s[j] for s in stereo_h],
+                    None if normal_h is None else normal_h[j]))
+    return out
+
+
+def core_generation_funnel(outpath, inputimages, inputdepthmaps, inputnames, inp, ops=None):
     if len(inputimages) == 0 or inputimages[0] is None:
         return
     if inputdepthmaps is None or len(inputdepthmaps) == 0:
@@ -228,8 +294,6 @@ def core_generation_funnel(outpath, inputimages, inputdepthmaps, inputnames, inp
     for name in _OUT_OF_SCOPE:
         if inp[name]:
             raise NotImplementedError(f"{name} is outside the depthmap_b200 hot path (SURVEY.md §8); use the reference for it")
-    if inp[go.BOOST]:
-        raise NotImplementedError("BOOST (multi-resolution merge) is not implemented in depthmap_b200 yet")
     holder = get_model_holder()
     if ops is None:
         ops = {}
@@ -239,83 +303,59 @@ def core_generation_funnel(outpath, inputimages, inputdepthmaps, inputnames, inp
     try:
         if not inputdepthmaps_complete:
             holder.ensure_models(inp[go.MODEL_TYPE], dev, inp[go.BOOST], inp[go.TILING_MODE])
-        # single channel input (PIL mode I) -> RGB, as src/core.py:135-137
+        # single channel input (PIL mode I) -> RGB, as src/core.py:135-137 (the caller's list is updated, like the reference)
         for i in range(len(inputimages)):
             if inputimages[i].mode == 'I':
                 inputimages[i] = inputimages[i].convert('RGB')
 
-        # batch images of equal size (the reference loop is serial; results are identical per image)
-        groups = {}
-        for i, im in enumerate(inputimages):
-            groups.setdefault((im.width, im.height, inputdepthmaps[i] is not None), []).append(i)
-        ready = {}
-        for (w, h, custom), idxs in groups.items():
-            rgbs = [np.asarray(inputimages[i].convert('RGB') if inputimages[i].mode != 'RGB' else inputimages[i]) for i in idxs]
-            rgb_t = torch.from_numpy(np.stack(rgbs)).to(dev, non_blocking=True)
-            preds = None
-            if custom:
-                outs = [_custom_depth_to_unit(inputdepthmaps[i], inputimages[i]) for i in idxs]
-                t = torch.from_numpy(np.stack(outs)).to(dev)
-                q = torch.clamp(t * 65536 + 0.0001, 0, 65536 - 0.1).to(torch.int32)
-                depth_u16 = q.to(torch.int16).view(torch.uint16)  # values < 65536: the int16 wrap is the uint16 bit pattern
-            else:
-                if inp[go.NET_SIZE_MATCH]:
-                    net_width, net_height = (w + 31) // 32 * 32, (h + 31) // 32 * 32
-                else:
-                    net_width, net_height = inp[go.NET_WIDTH], inp[go.NET_HEIGHT]
-                preds, invert = holder.get_raw_prediction_batch(rgb_t, net_width, net_height)
-                depth_u16, flags = normalize_prediction_batch(
-                    preds, invert, inp[go.CLIPDEPTH], inp[go.CLIPDEPTH_MODE], inp[go.CLIPDEPTH_FAR],
-                    inp[go.CLIPDEPTH_NEAR], return_flags=True)
-            stereo = None
-            if inp[go.GEN_STEREO]:
-                stereo = create_stereoimages_batch(
-                    rgb_t, depth_u16, inp[go.STEREO_DIVERGENCE], inp[go.STEREO_SEPARATION], inp[go.STEREO_MODES],
-                    inp[go.STEREO_BALANCE], inp[go.STEREO_OFFSET_EXPONENT], inp[go.STEREO_FILL_ALGO])
-            normal = None
-            if inp[go.GEN_NORMALMAP]:
-                normal = create_normalmap_batch(
-                    depth_u16,
-                    inp[go.NORMALMAP_PRE_BLUR_KERNEL] if inp[go.NORMALMAP_PRE_BLUR] else None,
-                    inp[go.NORMALMAP_SOBEL_KERNEL] if inp[go.NORMALMAP_SOBEL] else None,
-                    inp[go.NORMALMAP_POST_BLUR_KERNEL] if inp[go.NORMALMAP_POST_BLUR] else None,
-                    inp[go.NORMALMAP_INVERT])
-            # one device -> host transfer per tensor per group
-            depth_h = depth_u16.cpu().numpy()
-            preds_h = preds.cpu().numpy() if preds is not None else None
-            flags_h = flags.cpu().numpy() if preds is not None else None
-            stereo_h = [s.cpu().numpy() for s in stereo] if stereo is not None else None
-            normal_h = normal.cpu().numpy() if normal is not None else None
-            for j, i in enumerate(idxs):
-                ready[i] = (rgbs[j], depth_h[j], None if preds_h is None else (preds_h[j], invert, int(flags_h[j])),
-                            None if stereo_h is None else [s[j] for s in stereo_h],
-                            None if normal_h is None else normal_h[j])
-
-        # yield in the reference's order (src/core.py:194-305)
+        # The reference loop is strictly serial (src/core.py:133).  Here consecutive images of equal size (and equal
+        # "has a custom depth map" state) form one batch of at most max_batch_for(w, h) images; batches are processed and
+        # yielded in input order, so results stream out lazily and host / device memory stay bounded for long clips.
         modes = inp[go.STEREO_MODES]
-        for count in range(len(inputimages)):
-            rgb, img_output, pred, stereo, normal = ready[count]
-            if pred is not None and inp[go.DO_OUTPUT_DEPTH_PREDICTION] and not pred[2]:
-                p = np.copy(pred[0])
-                if pred[1]:
-                    p *= -1
-                yield count, 'depth_prediction', p
-            if inp[go.DO_OUTPUT_DEPTH]:
-                img_depth = np.bitwise_not(img_output) if inp[go.OUTPUT_DEPTH_INVERT] else img_output
-                if inp[go.OUTPUT_DEPTH_COMBINE]:
-                    axis = 1 if inp[go.OUTPUT_DEPTH_COMBINE_AXIS] == 'Horizontal' else 0
-                    yield count, 'concat_depth', Image.fromarray(
-                        np.concatenate((rgb, convert_i16_to_rgb(img_depth, rgb)), axis=axis))
-                else:
-                    yield count, 'depth', Image.fromarray(img_depth)
-            if stereo is not None:
-                for c in range(len(stereo)):
-                    yield count, modes[c], Image.fromarray(stereo[c])
-            if normal is not None:
-                yield count, 'normalmap', Image.fromarray(normal)
+        n = len(inputimages)
+        count = 0
+        while count < n:
+            im0 = inputimages[count]
+            key = (im0.width, im0.height, inputdepthmaps[count] is not None)
+            cap = max_batch_for(im0.width, im0.height)
+            idxs = [count]
+            while (len(idxs) < cap and idxs[-1] + 1 < n and
+                   (inputimages[idxs[-1] + 1].width, inputimages[idxs[-1] + 1].height,
+                    inputdepthmaps[idxs[-1] + 1] is not None) == key):
+                idxs.append(idxs[-1] + 1)
+            results = _process_chunk(holder, inp, dev, inputimages, inputdepthmaps, idxs)
+            # yield in the reference's order (src/core.py:194-305)
+            for i, (rgb, img_output, pred, stereo, normal) in zip(idxs, results):
+                if pred is not None and inp[go.DO_OUTPUT_DEPTH_PREDICTION] and not pred[2]:
+                    p = np.copy(pred[0])
+                    if pred[1]:
+                        p *= -1
+                    yield i, 'depth_prediction', p
+                if inp[go.DO_OUTPUT_DEPTH]:
+                    img_depth = np.bitwise_not(img_output) if inp[go.OUTPUT_DEPTH_INVERT] else img_output
+                    if inp[go.OUTPUT_DEPTH_COMBINE]:
+                        axis = 1 if inp[go.OUTPUT_DEPTH_COMBINE_AXIS] == 'Horizontal' else 0
+                        yield i, 'concat_depth', Image.fromarray(
+                            np.concatenate((rgb, convert_i16_to_rgb(img_depth, rgb)), axis=axis))
+                    else:
+                        yield i, 'depth', Image.fromarray(img_depth)
+                if stereo is not None:
+                    for c in range(len(stereo)):
+                        yield i, modes[c], Image.fromarray(stereo[c])
+                if normal is not None:
+                    yield i, 'normalmap', Image.fromarray(normal)
+            count = idxs[-1] + 1
     except Exception as e:
         if 'out of memory' in str(e).lower():
-            raise Exception("out of GPU memory, could not generate depthmap! Reduce the batch or the net size. (" + str(e) + ")")
+            # src/core.py:310-326: the reference replaces the error by its list of suggestions
+            suggestion = "out of GPU memory, could not generate depthmap! Here are some suggestions to work around this issue:\n"
+            if inp[go.BOOST]:
+                suggestion += " * Disable BOOST (generation will be faster, but the depthmap will be less detailed)\n"
+            suggestion += " * Use a different model (generally, more memory-consuming models produce better depthmaps)\n"
+            if not inp[go.BOOST]:
+                suggestion += " * Reduce net size (this could reduce quality)\n"
+            suggestion += " * Lower DEPTHMAP_B200_MAX_BATCH (images per device batch)\n"
+            raise Exception(suggestion)
         raise
     finally:
         if ops.get('depthmap_script_keepmodels', True):
