@@ -52,237 +52,6 @@ constexpr int AT_STAGES = 2;
 constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + AT_P_BYTES + 256;  // base is __align__(1024); 2 CTAs fit one SM
 constexpr int AT_TMEM_COLS = 256;                   // S: cols [0,128), PV staging: cols [128,192)
 
-template <bool HAS_BIAS>
-__global__ void __launch_bounds__(192, 2) attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *sQ = smem;
-    uint8_t *sKV = sQ + AT_Q_BYTES;                       // stage s: K at sKV + s*32K, V at +16K
-    uint8_t *sP = sKV + AT_STAGES * 2 * AT_KV_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + AT_P_BYTES);
-    uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *p_full = bars + 6, *pv_full = bars + 7;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 8);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int q0 = qt * AT_BQ;
-    const int num_kv = (p.N + AT_BKV - 1) / AT_BKV;
-    const int row_base = b * p.N;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmQKV);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
-        mbar_init(pv_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_ptr, AT_TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 128;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
-            tma_load_2d(sQ, &tmQKV, q_full, h * AT_D, row_base + q0);
-            for (int j = 0; j < num_kv; ++j) {
-                const int s = j & 1;
-                mbar_wait_backoff(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-                uint8_t *sk = sKV + s * 2 * AT_KV_BYTES, *sv = sk + AT_KV_BYTES;
-                mbar_arrive_expect_tx(&kv_full[s], 2 * AT_KV_BYTES);
-                tma_load_2d(sk, &tmQKV, &kv_full[s], p.C + h * AT_D, row_base + j * AT_BKV);
-                tma_load_2d(sv, &tmQKV, &kv_full[s], 2 * p.C + h * AT_D, row_base + j * AT_BKV);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = make_idesc_f16(AT_BQ, AT_BKV, 0, 0, 0);
-            constexpr uint32_t idesc_pv = make_idesc_f16(AT_BQ, AT_D, 0, 0, 1);  // B (= V) is MN-major
-            mbar_wait_backoff(q_full, 0);
-            const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ));
-            const uint32_t sp = smem_u32(sP);
-            for (int j = 0; j < num_kv; ++j) {
-                const int s = j & 1;
-                mbar_wait_backoff(&kv_full[s], (j >> 1) & 1);
-                tc_fence_after();
-                const uint32_t sk = smem_u32(sKV + s * 2 * AT_KV_BYTES), sv = sk + AT_KV_BYTES;
-                const uint64_t kdesc = make_desc_kmajor_sw128(sk);
-#pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_f16(tmem_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_qk, k != 0);
-                umma_commit(s_full);
-                mbar_wait_backoff(p_full, j & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < AT_BKV / 16; ++k) {
-                    const uint64_t pdesc = make_desc_kmajor_sw128(sp + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32);
-                    const uint64_t vdesc = make_desc_mnmajor_sw128(sv + k * 16 * 128, 16 * 128);
-                    umma_f16(tmem_PV, pdesc, vdesc, idesc_pv, k != 0);
-                }
-                umma_commit(pv_full);
-                umma_commit(&kv_empty[s]);
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const int qi = q0 + row;                       // query index inside the image
-        float m_run = -INFINITY, l_run = 0.f;
-        float o[AT_D];
-#pragma unroll
-        for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
-        const __half *brow = HAS_BIAS ? p.bias + ((size_t)h * p.N + (qi < p.N ? qi : 0)) * p.bias_ld : nullptr;
-        constexpr float LOG2E = 1.4426950408889634f;
-
-        for (int j = 0; j < num_kv; ++j) {
-            const int kbase = j * AT_BKV;
-            const int nvalid = min(AT_BKV, p.N - kbase);
-            const bool full_tile = nvalid == AT_BKV;
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            // ---- pass 1: row max (log2 domain).  Without bias max(scale*s) = scale*max(s) since scale > 0 ----
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
-                if (c0 >= nvalid) break;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + lane_off + c0, r);
-                tmem_ld_wait();
-                if (HAS_BIAS) {
-                    const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const uint4 u = __ldg(bp + g);
-                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 bf = __half22float2(h2[k]);
-                            const int i = g * 8 + 2 * k;
-                            float s0 = fmaf(bf.x, LOG2E, __uint_as_float(r[i]) * p.scale_log2e);
-                            float s1 = fmaf(bf.y, LOG2E, __uint_as_float(r[i + 1]) * p.scale_log2e);
-                            if (!full_tile) { s0 = (c0 + i < nvalid) ? s0 : -INFINITY; s1 = (c0 + i + 1 < nvalid) ? s1 : -INFINITY; }
-                            mx = fmaxf(mx, fmaxf(s0, s1));
-                        }
-                    }
-                } else if (full_tile) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c0 + i < nvalid) ? __uint_as_float(r[i]) : -INFINITY);
-                }
-            }
-            if (!HAS_BIAS) mx *= p.scale_log2e;
-            // ---- fold in PV of the previous tile, then rescale ----
-            if (j > 0) {
-                mbar_wait(pv_full, (j - 1) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < AT_D; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_PV + lane_off + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o[c0 + i] += __uint_as_float(r[i]);
-                }
-            }
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = ex2_approx(m_run - m_new);
-            l_run *= alpha;
-#pragma unroll
-            for (int d = 0; d < AT_D; ++d) o[d] *= alpha;
-            m_run = m_new;
-            // ---- pass 2: P = exp2(scale*s [+ bias] - m), fp16, into the swizzled K-major smem tile ----
-            float lsum = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
-                uint32_t packed[16];
-                if (c0 < nvalid) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_S + lane_off + c0, r);
-                    tmem_ld_wait();
-                    float pv[32];
-                    if (HAS_BIAS) {
-                        const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint4 u = __ldg(bp + g);
-                            const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float2 bf = __half22float2(h2[k]);
-                                const int i = g * 8 + 2 * k;
-                                pv[i] = ex2_approx(fmaf(bf.x, LOG2E, fmaf(__uint_as_float(r[i]), p.scale_log2e, -m_new)));
-                                pv[i + 1] = ex2_approx(fmaf(bf.y, LOG2E, fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -m_new)));
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2e, -m_new));
-                    }
-                    if (!full_tile) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) pv[i] = (c0 + i < nvalid) ? pv[i] : 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const __half2 h2 = __floats2half2_rn(pv[i], pv[i + 1]);
-                        // the sum must match what the MMA sees: accumulate the fp16-rounded probabilities
-                        const float2 f2 = __half22float2(h2);
-                        lsum += f2.x + f2.y;
-                        packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) packed[i] = 0u;
-                }
-                // 32 keys = 64 B = four 16-byte chunks of atom (c0 / 64), chunk index ((c0 % 64) / 8 + t) ^ (row % 8)
-                uint8_t *atom = sP + (c0 >> 6) * (AT_BQ * 128) + row * 128;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int chunk = (((c0 & 63) >> 3) + t) ^ (row & 7);
-                    *reinterpret_cast<uint4 *>(atom + chunk * 16) = make_uint4(packed[4 * t], packed[4 * t + 1], packed[4 * t + 2], packed[4 * t + 3]);
-                }
-            }
-            l_run += lsum;
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(p_full);
-        }
-        // ---- last PV, normalise, store ----
-        mbar_wait(pv_full, (num_kv - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < AT_D; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_PV + lane_off + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[c0 + i] += __uint_as_float(r[i]);
-        }
-        if (qi < p.N) {
-            const float inv = 1.0f / l_run;
-            __half *dst = p.out + (size_t)(row_base + qi) * p.C + h * AT_D;
-#pragma unroll
-            for (int d = 0; d < AT_D; d += 8) {
-                uint4 u;
-                __half2 *h2 = reinterpret_cast<__half2 *>(&u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(o[d + 2 * k] * inv, o[d + 2 * k + 1] * inv);
-                *reinterpret_cast<uint4 *>(dst + d) = u;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, AT_TMEM_COLS);
-}
-
-
 // =====================================================================================================================
 // Ping-pong variant (the default): one CTA owns TWO 128-query tiles of one (head, image) and runs two softmax
 // warpgroups.  While warpgroup A exponentiates S_A(j) the tensor core computes S_B(j) = Q_B K_j^T and P_A V_j, so the
@@ -351,340 +120,6 @@ __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
 
 struct TagTrue { static constexpr bool value = true; };
 struct TagFalse { static constexpr bool value = false; };
-
-template <int BIAS_MODE>
-__global__ void __launch_bounds__(A2_THREADS, 1) attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, Attn2Params pp) {
-    const AttnParams &p = pp.a;
-    constexpr bool ALIGNED = BIAS_MODE == 3;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *sQ = smem_raw;                                  // tile A at +0, tile B at +16 KB
-    uint8_t *sKV = sQ + A2_Q_BYTES;
-    uint8_t *sP = sKV + A2_KV_BYTES;                         // P_A at +0, P_B at +32 KB
-    uint8_t *sOnes = sP + A2_P_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sOnes + A2_ONES_BYTES);
-    uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3;
-    uint64_t *s_full = bars + 5, *p_full = bars + 7, *pv_full = bars + 9;   // [2] each, index = group
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 11);
-    float *s_tab = reinterpret_cast<float *>(smem_raw + A2_SMEM_BASE);
-    uint16_t *s_koff = reinterpret_cast<uint16_t *>(smem_raw + A2_SMEM_BASE + 16384);   // mode 2: per key; mode 3: per 16-key chunk
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    // token geometry.  ALIGNED: tiles cover tokens 1 .. N-1 (the patch grid); key 0 (class token) is the tail tile.
-    const int tok0 = ALIGNED ? 1 : 0;
-    const int ntok = p.N - tok0;
-    const int num_main = (ntok + AT_BKV - 1) / AT_BKV;
-    const int num_kv = num_main + (ALIGNED ? 1 : 0);
-    const int q0 = qp * 2 * AT_BQ;                            // first query of the CTA, relative to tok0
-    const bool b_active = q0 + AT_BQ < ntok;                  // second tile may be entirely out of range
-    const int row_base = b * p.N;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmQKV);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 128); mbar_init(&pv_full[g], 1); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_ptr, 512);
-    for (int i = threadIdx.x; i < A2_ONES_BYTES / 4; i += A2_THREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3c003c00u;
-    if (BIAS_MODE >= 2) {
-        const float *tab = pp.rel_table + (size_t)h * pp.nrd;
-        for (int i = threadIdx.x; i < pp.nrd; i += A2_THREADS) s_tab[i] = __ldg(tab + i);
-        if (ALIGNED) {
-            for (int c = threadIdx.x; c < num_main * (AT_BKV / 16); c += A2_THREADS) {
-                const int t = c * 16;
-                s_koff[c] = (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw));
-            }
-        } else {
-            for (int k = threadIdx.x; k < num_kv * AT_BKV; k += A2_THREADS) {
-                const int t = k - 1;
-                s_koff[k] = (k >= 1 && k < p.N) ? (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw)) : (uint16_t)0;
-            }
-        }
-    }
-    fence_proxy_async();          // the ones block is read by the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, b_active ? 2 * AT_Q_BYTES : AT_Q_BYTES);
-            tma_load_2d(sQ, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0);
-            if (b_active) tma_load_2d(sQ + AT_Q_BYTES, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0 + AT_BQ);
-            for (int j = 0; j < num_kv; ++j) {
-                const int s = j & 1;
-                const int key0 = (ALIGNED && j == num_main) ? 0 : tok0 + j * AT_BKV;
-                mbar_wait_backoff(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-                uint8_t *sk = sKV + s * 2 * AT_KV_BYTES, *sv = sk + AT_KV_BYTES;
-                mbar_arrive_expect_tx(&kv_full[s], 2 * AT_KV_BYTES);
-                tma_load_2d(sk, &tmQKV, &kv_full[s], p.C + h * AT_D, row_base + key0);
-                tma_load_2d(sv, &tmQKV, &kv_full[s], 2 * p.C + h * AT_D, row_base + key0);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_pv = make_idesc_f16(AT_BQ, A2_PV_N, 0, 0, 1);  // B (= V | ones) is MN-major
-            const uint32_t ones_addr = smem_u32(sOnes);
-            mbar_wait_backoff(q_full, 0);
-            const int ngroups = b_active ? 2 : 1;
-            auto tile_cols = [&](int j) {
-                const int nvalid = (ALIGNED && j == num_main) ? 1 : min(AT_BKV, ntok - j * AT_BKV);
-                return (nvalid + 15) & ~15;
-            };
-            // S_g(j) = Q_g K_j^T into the S buffer of group g (free once p_full[g](j-1) has arrived)
-            auto issue_s = [&](int g, int j) {
-                const uint32_t idesc_qk = make_idesc_f16(AT_BQ, tile_cols(j), 0, 0, 0);
-                const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sKV + (j & 1) * 2 * AT_KV_BYTES));
-                const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ + g * AT_Q_BYTES));
-#pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k)
-                    umma_f16(tmem_base + g * 128, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_qk, k != 0);
-                umma_commit(&s_full[g]);
-            };
-            // Issue order per group: PV_g(j) and then S_g(j+1) straight away, as soon as group g has handed over P_g(j).
-            // The two softmax groups therefore drift half a step apart: while A exponentiates, the tensor core runs B's
-            // PV / next S, and neither group waits for the OTHER group's softmax before getting its next scores.
-            mbar_wait_backoff(&kv_full[0], 0);
-            tc_fence_after();
-            for (int g = 0; g < ngroups; ++g) issue_s(g, 0);
-            for (int j = 0; j < num_kv; ++j) {
-                const int s = j & 1;
-                const int ncols = tile_cols(j);
-                const bool has_next = j + 1 < num_kv;
-                const uint32_t sv = smem_u32(sKV + s * 2 * AT_KV_BYTES) + AT_KV_BYTES;
-                for (int g = 0; g < ngroups; ++g) {   // PV_g = P_g [V_j | 1] once group g has written P_g
-                    mbar_wait_backoff(&p_full[g], j & 1);
-                    tc_fence_after();
-                    const uint32_t sp = smem_u32(sP + g * AT_P_BYTES);
-                    for (int k = 0; k < (ncols >> 4); ++k) {
-                        const uint64_t pdesc = make_desc_kmajor_sw128(sp + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32);
-                        const uint32_t vaddr = sv + k * 16 * 128;
-                        const uint64_t vdesc = make_desc_mnmajor_sw128(vaddr, ones_addr - vaddr);   // second 64-wide MN block = ones
-                        umma_f16(tmem_base + 256 + g * A2_PV_STRIDE, pdesc, vdesc, idesc_pv, k != 0);
-                    }
-                    umma_commit(&pv_full[g]);
-                    if (has_next) {
-                        if (g == 0) { mbar_wait_backoff(&kv_full[s ^ 1], ((j + 1) >> 1) & 1); tc_fence_after(); }
-                        issue_s(g, j + 1);
-                    }
-                }
-                umma_commit(&kv_empty[s]);
-            }
-        }
-    } else {
-        const int g = (warp - 2) >> 2;            // softmax group: 0 = tile A, 1 = tile B
-        if (g == 1 && !b_active) goto done;
-        {
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const uint32_t tmem_S = tmem_base + g * 128 + lane_off, tmem_PV = tmem_base + 256 + g * A2_PV_STRIDE + lane_off;
-        uint8_t *sPg = sP + g * AT_P_BYTES;
-        const int tq = q0 + g * AT_BQ + row;           // query, relative to tok0
-        const bool q_ok = tq < ntok;
-        const int qi = tok0 + tq;                      // query index inside the image
-        float m_run = -INFINITY;
-        float o[AT_D + 1];                             // o[64] = running row sum
-#pragma unroll
-        for (int d = 0; d <= AT_D; ++d) o[d] = 0.f;
-        constexpr float LOG2E = 1.4426950408889634f;
-        const __half *brow = BIAS_MODE == 1 ? p.bias + ((size_t)h * p.N + (q_ok ? qi : 0)) * p.bias_ld : nullptr;
-        // relative-position table addressing: idx(q, k) = base_q - mult * koff_k; generic mode: the class-token query uses
-        // the constant entry nrd-3 (mult = 0); the class-token key (k = 0) is patched separately below
-        int rp_base = 0, rp_mult = 1;
-        float rp_k0 = 0.f;                                   // bias of (q, key 0)
-        float rp_rowmax = 0.f;
-        if (BIAS_MODE >= 2) {
-            const int qq = q_ok ? qi : 1;
-            rp_rowmax = __ldg(pp.rel_rowmax + (size_t)h * p.N + qq);
-            if (qq == 0) { rp_base = pp.nrd - 3; rp_mult = 0; rp_k0 = s_tab[pp.nrd - 1]; }
-            else {
-                const int t = qq - 1, qy = t / pp.gw, qx = t % pp.gw;
-                rp_base = (qy + pp.gh - 1) * (2 * pp.gw - 1) + (qx + pp.gw - 1);
-                rp_k0 = s_tab[pp.nrd - 2];
-            }
-        }
-        const uint64_t scale2 = pack2(p.scale_log2e, p.scale_log2e);
-
-        // fold the finished PV accumulator (64 dims + the row-sum column) of the previous tile into the registers
-        auto fold_pv = [&]() {
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32(tmem_PV, r0);
-            tmem_ld_32x32(tmem_PV + 32, r1);
-            const uint32_t rs = tmem_ld_32x1(tmem_PV + 64);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { o[i] += __uint_as_float(r0[i]); o[32 + i] += __uint_as_float(r1[i]); }
-            o[AT_D] += __uint_as_float(rs);
-        };
-
-        for (int j = 0; j < num_kv; ++j) {
-            const bool tail = ALIGNED && j == num_main;
-            const int kbase = tail ? 0 : tok0 + j * AT_BKV;                 // first key (token index) of the tile
-            const int nvalid = tail ? 1 : min(AT_BKV, ntok - j * AT_BKV);
-            const int ncols = (nvalid + 15) & ~15;
-            mbar_wait(&s_full[g], j & 1);
-            tc_fence_after();
-            // ---- first tile only: a real max pass (m_run starts at -inf).  Later tiles use LAZY rescaling: P is
-            // formed against the running max as it stands, the tile max is tracked on the side, and only if it exceeds
-            // the running max by more than 2^8 is the tile redone with the new max (rare; keeps P inside fp16 range).
-            if (j == 0) {
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c0 = 0; c0 < AT_BKV; c0 += 32) {
-                    if (c0 >= nvalid) break;
-                    const bool full32 = c0 + 32 <= nvalid;
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_S + c0, r);
-                    tmem_ld_wait();
-                    if (BIAS_MODE == 1) {
-                        const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
-#pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            const uint4 u = __ldg(bp + gq);
-                            const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float2 bf = __half22float2(h2[k]);
-                                const int i = gq * 8 + 2 * k;
-                                float s0 = fmaf(bf.x, LOG2E, __uint_as_float(r[i]) * p.scale_log2e);
-                                float s1 = fmaf(bf.y, LOG2E, __uint_as_float(r[i + 1]) * p.scale_log2e);
-                                if (!full32) { s0 = (c0 + i < nvalid) ? s0 : -INFINITY; s1 = (c0 + i + 1 < nvalid) ? s1 : -INFINITY; }
-                                mx = fmaxf(mx, fmaxf(s0, s1));
-                            }
-                        }
-                    } else if (full32) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c0 + i < nvalid) ? __uint_as_float(r[i]) : -INFINITY);
-                    }
-                }
-                if (BIAS_MODE == 0) mx *= p.scale_log2e;
-                if (BIAS_MODE >= 2) mx = fmaf(mx, p.scale_log2e, rp_rowmax);   // upper bound: max(scale*s) + max(bias)
-                m_run = mx;
-            } else {
-                // fold in PV of the previous tile (computed against the same m_run: no rescale needed yet)
-                mbar_wait(&pv_full[g], (j - 1) & 1);
-                tc_fence_after();
-                fold_pv();
-            }
-            // ---- P = exp2(scale*s [+ bias] - m_run) as fp16 into the swizzled K-major smem tile ----
-            float mx_rel;                          // max over the tile of (score - m_run)
-            for (int attempt = 0;; ++attempt) {
-                mx_rel = -INFINITY;
-                const float neg_m = -m_run;
-                const uint64_t negm2 = pack2(neg_m, neg_m);
-                // one 16-column chunk: scores -> probabilities -> two 16-byte stores into the P tile
-                auto chunk = [&](const uint32_t (&r)[16], int c0, auto partial_tag) {
-                    constexpr bool PARTIAL = decltype(partial_tag)::value;   // only the last chunk of a ragged tile masks
-                    float bv[16];
-                    if (BIAS_MODE == 1) {
-                        const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
-#pragma unroll
-                        for (int gq = 0; gq < 2; ++gq) {
-                            const uint4 u = __ldg(bp + gq);
-                            const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) { const float2 bf = __half22float2(h2[k]); bv[gq * 8 + 2 * k] = bf.x * LOG2E; bv[gq * 8 + 2 * k + 1] = bf.y * LOG2E; }
-                        }
-                    } else if (BIAS_MODE == 2) {
-                        const uint4 *kp = reinterpret_cast<const uint4 *>(s_koff + kbase + c0);
-#pragma unroll
-                        for (int gq = 0; gq < 2; ++gq) {
-                            const uint4 u = kp[gq];
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                bv[gq * 8 + 2 * k] = s_tab[rp_base - rp_mult * (int)(w[k] & 0xffffu)];
-                                bv[gq * 8 + 2 * k + 1] = s_tab[rp_base - rp_mult * (int)(w[k] >> 16)];
-                            }
-                        }
-                        if (kbase + c0 == 0) bv[0] = rp_k0;
-                    } else if (BIAS_MODE == 3) {
-                        if (tail) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) bv[i] = rp_k0;
-                        } else {
-                            const float *tp = s_tab + (rp_base - (int)s_koff[(j * AT_BKV + c0) >> 4]);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) bv[i] = *(tp - i);
-                        }
-                    }
-                    uint32_t packed[8];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const uint64_t b2 = BIAS_MODE == 0 ? negm2 : add2(pack2(bv[i], bv[i + 1]), negm2);
-                        float t0, t1;
-                        unpack2(fma2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, b2), t0, t1);
-                        if (PARTIAL) { t0 = (c0 + i < nvalid) ? t0 : -INFINITY; t1 = (c0 + i + 1 < nvalid) ? t1 : -INFINITY; }
-                        mx_rel = max3(mx_rel, t0, t1);
-                        const __half2 h2 = __floats2half2_rn(ex2_approx(t0), ex2_approx(t1));
-                        packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
-                    }
-                    // 16 keys = 32 B = two 16-byte chunks of atom (c0 / 64), chunk index ((c0 % 64) / 8 + t) ^ (row % 8)
-                    uint8_t *atom = sPg + (c0 >> 6) * (AT_BQ * 128) + row * 128;
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const int ch = (((c0 & 63) >> 3) + t) ^ (row & 7);
-                        *reinterpret_cast<uint4 *>(atom + ch * 16) = make_uint4(packed[4 * t], packed[4 * t + 1], packed[4 * t + 2], packed[4 * t + 3]);
-                    }
-                };
-                // two register buffers, alternating: the TMEM load of chunk c+1 is in flight while chunk c is exponentiated
-                uint32_t ra[16], rb[16];
-                tmem_ld_32x16(tmem_S, ra);
-#pragma unroll 1
-                for (int c0 = 0; c0 < ncols; c0 += 32) {
-                    tmem_ld_wait();
-                    const bool has_b = c0 + 16 < ncols;
-                    if (has_b) tmem_ld_32x16(tmem_S + c0 + 16, rb);
-                    if (c0 + 16 > nvalid) chunk(ra, c0, TagTrue()); else chunk(ra, c0, TagFalse());
-                    if (has_b) {
-                        tmem_ld_wait();
-                        if (c0 + 32 < ncols) tmem_ld_32x16(tmem_S + c0 + 32, ra);
-                        if (c0 + 32 > nvalid) chunk(rb, c0 + 16, TagTrue()); else chunk(rb, c0 + 16, TagFalse());
-                    }
-                }
-                const bool need = mx_rel > 8.0f;
-                if (!__any_sync(0xffffffffu, need)) break;
-                if (need) {   // raise this row's running max and rescale what has been accumulated so far
-                    const float alpha = ex2_approx(-mx_rel);
-#pragma unroll
-                    for (int d = 0; d <= AT_D; ++d) o[d] *= alpha;
-                    m_run += mx_rel;
-                }
-            }
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(&p_full[g]);
-        }
-        // ---- last PV, normalise, store ----
-        mbar_wait(&pv_full[g], (num_kv - 1) & 1);
-        tc_fence_after();
-        fold_pv();
-        if (q_ok) {
-            const float inv = 1.0f / o[AT_D];
-            __half *dst = p.out + (size_t)(row_base + qi) * p.C + h * AT_D;
-#pragma unroll
-            for (int d = 0; d < AT_D; d += 8) {
-                uint4 u;
-                __half2 *h2 = reinterpret_cast<__half2 *>(&u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(o[d + 2 * k] * inv, o[d + 2 * k + 1] * inv);
-                *reinterpret_cast<uint4 *>(dst + d) = u;
-            }
-        }
-        }
-    }
-done:
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
 
 // =====================================================================================================================
 // Two-threads-per-row variant (the default): same tiling, barriers and MMA schedule as attention_fwd2_kernel, but every
@@ -1105,30 +540,432 @@ __global__ void __launch_bounds__(256) attention_cls_row_kernel(const __half *__
     }
 }
 
-template <int MODE>
-static int launch_attn2(const CUtensorMap &tm, const Attn2Params &pp, cudaStream_t stream, const __half *qkv) {
-    static int one_thread_rows = -1;     // DEPTHMAP_B200_ATTN_FWD2=1: the one-thread-per-row kernel (kept for comparison)
-    if (one_thread_rows < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_FWD2"); one_thread_rows = (e && e[0] == '1') ? 1 : 0; }
-    const int ntok = pp.a.N - (MODE == 3 ? 1 : 0);
-    dim3 grid((ntok + 2 * AT_BQ - 1) / (2 * AT_BQ), pp.a.H, pp.a.B);
-    if (one_thread_rows) {
-        const int smem = A2_SMEM_BASE + (MODE >= 2 ? A2_TAB_BYTES : 0);
-        static bool configured = false;
-        if (!configured) {
-            DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured = true;
+// =====================================================================================================================
+// attention_fwd4_kernel (the default).  Same tiling as fwd3 (one CTA = two 128-query tiles of one (head, image), two
+// threads per query row, P through the swizzled K-major smem tile, PV with N = 80 whose ones block yields the row sums),
+// restructured around what the round-1 profile showed (softmax warps idle 25% of the time waiting for the next S,
+// 15.6 issued instructions per exponential where the MUFU pipe allows 8):
+//   * S leaves TMEM at once: a thread loads its 64 scores of the tile into registers and the warp releases the S
+//     accumulator (s_free) BEFORE any arithmetic, so S(j+1) = Q K_{j+1}^T is computed while tile j is exponentiated;
+//   * O stays in TMEM: PV(j) accumulates in place (no per-tile fold of 33 fp32 adds per thread); the rare lazy-max bump
+//     rescales the accumulator with tcgen05.ld / tcgen05.st between PV(j-1) and PV(j);
+//   * one pass per tile, never a recompute: u = s*scale + bias - m_run for all 64 scores, exact row max through the pair
+//     mailbox, and if the max exceeds the lazy threshold (or at tile 0) the 64 values are shifted in registers;
+//   * one MMA issuer per query tile (warps 1 and 2), each a plain sequential loop  S(j) -> PV(j-1), separate K and V
+//     rings so K_{j+1} is released after S(j) and not after PV(j);
+//   * BEiT bias (mode 3): the head's table is held REVERSED, twice (the second copy shifted by one element), so the 16
+//     consecutive biases of a 16-key chunk are eight 8-byte-aligned LDS.64 with immediate offsets;
+//   * warp-elected mbarrier arrivals (8 per tile instead of 256).
+//   warp 0: TMA producer | warp 1 / 2: MMA issuer of tile A / B | warp 3: idle | warps 4-19: softmax (as fwd3)
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,336) O_B [352,432); columns 64..79 of O are the ones block.
+// =====================================================================================================================
+constexpr int A4_THREADS = 128 + 512;
+constexpr int A4_Q_OFF = 0;                                   // 2 x 16 KB
+constexpr int A4_K_OFF = A4_Q_OFF + 2 * AT_Q_BYTES;           // 2 stages x 16 KB
+constexpr int A4_V_OFF = A4_K_OFF + 2 * AT_KV_BYTES;          // 2 stages x 16 KB
+constexpr int A4_P_OFF = A4_V_OFF + 2 * AT_KV_BYTES;          // 2 tiles x 32 KB
+constexpr int A4_ONES_OFF = A4_P_OFF + 2 * AT_P_BYTES;        // 2 KB of fp16 1.0
+constexpr int A4_BAR_OFF = A4_ONES_OFF + A2_ONES_BYTES;       // 256 B of mbarriers + the TMEM base
+constexpr int A4_XCH_OFF = A4_BAR_OFF + 256;                  // pair mailbox [slot][group][row][half] floats
+constexpr int A4_TAB_OFF = A4_XCH_OFF + A3_XCH_BYTES;         // relative-position table(s) + key offsets (modes 2, 3)
+constexpr int A4_SMEM_MAX = 227 * 1024;
+constexpr int A4_TAB_MAX = A4_SMEM_MAX - A4_TAB_OFF;
+constexpr int A4_O_COL = 256, A4_O_STRIDE = 96;
+
+__device__ __forceinline__ void mbar_wait_role(uint64_t *bar, uint32_t parity) {
+    // single-thread roles: block in hardware (suspend-time hint) instead of polling through the issue port
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int BIAS_MODE>
+__global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, Attn2Params pp) {
+    const AttnParams &p = pp.a;
+    constexpr bool ALIGNED = BIAS_MODE == 3;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *sQ = smem_raw + A4_Q_OFF, *sK = smem_raw + A4_K_OFF, *sV = smem_raw + A4_V_OFF, *sP = smem_raw + A4_P_OFF;
+    uint8_t *sOnes = smem_raw + A4_ONES_OFF;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + A4_BAR_OFF);
+    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7;
+    uint64_t *s_full = bars + 9, *s_free = bars + 11, *p_full = bars + 13, *pv_full = bars + 15;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 17);
+    float *s_xch = reinterpret_cast<float *>(smem_raw + A4_XCH_OFF);
+    float *s_tab = reinterpret_cast<float *>(smem_raw + A4_TAB_OFF);
+    const int nrd_pad = (pp.nrd + 3) & ~1;                    // even, >= nrd + 1: start of the shifted copy (mode 3)
+    uint16_t *s_koff = reinterpret_cast<uint16_t *>(s_tab + (ALIGNED ? 2 * nrd_pad : ((pp.nrd + 3) & ~3)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tok0 = ALIGNED ? 1 : 0;
+    const int ntok = p.N - tok0;
+    const int num_main = (ntok + AT_BKV - 1) / AT_BKV;
+    const int num_kv = num_main + (ALIGNED ? 1 : 0);
+    const int q0 = qp * 2 * AT_BQ;
+    const bool b_active = q0 + AT_BQ < ntok;
+    const int ngroups = b_active ? 2 : 1;
+    const int row_base = b * p.N;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQKV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], ngroups);
+            mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], ngroups);
         }
-        attention_fwd2_kernel<MODE><<<grid, A2_THREADS, smem, stream>>>(tm, pp);
-        DM_LAUNCH_CHECK("attention_fwd2_kernel");
+        for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 8); mbar_init(&p_full[g], 8); mbar_init(&pv_full[g], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    for (int i = threadIdx.x; i < A2_ONES_BYTES / 4; i += A4_THREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3c003c00u;
+    if (BIAS_MODE >= 2) {
+        const float *tab = pp.rel_table + (size_t)h * pp.nrd;
+        if (ALIGNED) {
+            // R0[x] = tab[nrd-1-x]; R1[x] = R0[x+1]
+            for (int i = threadIdx.x; i < pp.nrd; i += A4_THREADS) {
+                const float v = __ldg(tab + i);
+                const int x = pp.nrd - 1 - i;
+                s_tab[x] = v;
+                if (x >= 1) s_tab[nrd_pad + x - 1] = v;
+            }
+            for (int c = threadIdx.x; c < num_main * (AT_BKV / 16); c += A4_THREADS) {
+                const int t = c * 16;
+                s_koff[c] = (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw));
+            }
+        } else {
+            for (int i = threadIdx.x; i < pp.nrd; i += A4_THREADS) s_tab[i] = __ldg(tab + i);
+            for (int k = threadIdx.x; k < num_kv * AT_BKV; k += A4_THREADS) {
+                const int t = k - 1;
+                s_koff[k] = (k >= 1 && k < p.N) ? (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw)) : (uint16_t)0;
+            }
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto tile_cols = [&](int j) {
+        const int nvalid = (ALIGNED && j == num_main) ? 1 : min(AT_BKV, ntok - j * AT_BKV);
+        return (nvalid + 15) & ~15;
+    };
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (warp == 0 && lane == 0) {
+            mbar_arrive_expect_tx(q_full, b_active ? 2 * AT_Q_BYTES : AT_Q_BYTES);
+            tma_load_2d(sQ, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0);
+            if (b_active) tma_load_2d(sQ + AT_Q_BYTES, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0 + AT_BQ);
+            for (int j = 0; j < num_kv; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = ((j >> 1) & 1) ^ 1;
+                const int key0 = (ALIGNED && j == num_main) ? 0 : tok0 + j * AT_BKV;
+                mbar_wait_role(&k_empty[s], ph);
+                mbar_arrive_expect_tx(&k_full[s], AT_KV_BYTES);
+                tma_load_2d(sK + s * AT_KV_BYTES, &tmQKV, &k_full[s], p.C + h * AT_D, row_base + key0);
+                mbar_wait_role(&v_empty[s], ph);
+                mbar_arrive_expect_tx(&v_full[s], AT_KV_BYTES);
+                tma_load_2d(sV + s * AT_KV_BYTES, &tmQKV, &v_full[s], 2 * p.C + h * AT_D, row_base + key0);
+            }
+        } else if ((warp == 1 || (warp == 2 && b_active)) && lane == 0) {
+            const int g = warp - 1;
+            constexpr uint32_t idesc_pv = make_idesc_f16(AT_BQ, A2_PV_N, 0, 0, 1);
+            const uint32_t ones_addr = smem_u32(sOnes);
+            const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ + g * AT_Q_BYTES));
+            const uint32_t tmem_S = tmem_base + g * 128, tmem_O = tmem_base + A4_O_COL + g * A4_O_STRIDE;
+            mbar_wait_role(q_full, 0);
+            for (int j = 0; j <= num_kv; ++j) {
+                if (j < num_kv) {      // S(j) = Q K_j^T as soon as K_j has landed and the softmax warps hold S(j-1) in registers
+                    mbar_wait_role(&k_full[j & 1], (j >> 1) & 1);
+                    if (j > 0) mbar_wait_role(&s_free[g], (j - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t idesc_qk = make_idesc_f16(AT_BQ, tile_cols(j), 0, 0, 0);
+                    const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sK + (j & 1) * AT_KV_BYTES));
+#pragma unroll
+                    for (int k = 0; k < AT_D / 16; ++k)
+                        umma_f16(tmem_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_qk, k != 0);
+                    umma_commit(&s_full[g]);
+                    umma_commit(&k_empty[j & 1]);
+                }
+                if (j > 0) {           // O += P(j-1) V_{j-1}
+                    const int jj = j - 1;
+                    mbar_wait_role(&p_full[g], jj & 1);
+                    mbar_wait_role(&v_full[jj & 1], (jj >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t sp = smem_u32(sP + g * AT_P_BYTES);
+                    const uint32_t sv = smem_u32(sV + (jj & 1) * AT_KV_BYTES);
+                    const int nk = tile_cols(jj) >> 4;
+                    for (int k = 0; k < nk; ++k) {
+                        const uint64_t pdesc = make_desc_kmajor_sw128(sp + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32);
+                        const uint32_t vaddr = sv + k * 16 * 128;
+                        const uint64_t vdesc = make_desc_mnmajor_sw128(vaddr, ones_addr - vaddr);
+                        umma_f16(tmem_O, pdesc, vdesc, idesc_pv, (jj != 0 || k != 0) ? 1u : 0u);
+                    }
+                    umma_commit(&pv_full[g]);
+                    umma_commit(&v_empty[jj & 1]);
+                }
+            }
+        }
     } else {
-        const int smem = A3_SMEM_BASE + (MODE >= 2 ? A2_TAB_BYTES : 0);
-        static bool configured = false;
-        if (!configured) {
-            DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured = true;
+        // register pool: the CTA was launched with 640 x 96; the first warpgroup hands back 128 x (96 - 32), which lets
+        // the four softmax warpgroups grow to 112 (4 x 128 x 16 = 8192 <= 8192); asking for more blocks forever
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        const int idx = warp - 4;
+        const int g = idx >> 3, hh = (idx >> 2) & 1, q = idx & 3;
+        if (!(g == 1 && !b_active)) {
+        const int row = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const uint32_t tmem_S = tmem_base + g * 128 + lane_off + hh * 64;
+        const uint32_t tmem_O = tmem_base + A4_O_COL + g * A4_O_STRIDE + lane_off;
+        uint8_t *p_row = sP + g * AT_P_BYTES + hh * (AT_BQ * 128) + row * 128;   // this thread's 64 columns = one swizzle atom row
+        const uint32_t sw = (uint32_t)(row & 7) << 4;
+        const int pair_bar = 1 + g * 4 + q;
+        const int tq = q0 + g * AT_BQ + row;
+        const bool q_ok = tq < ntok;
+        const int qi = tok0 + tq;
+        float m_run = 0.f;
+        constexpr float LOG2E = 1.4426950408889634f;
+        const __half *brow = BIAS_MODE == 1 ? p.bias + ((size_t)h * p.N + (q_ok ? qi : 0)) * p.bias_ld : nullptr;
+        int rp_base = 0, rp_mult = 1, rp_e0 = 0;
+        float rp_k0 = 0.f;
+        if (BIAS_MODE >= 2) {
+            const int qq = q_ok ? qi : 1;
+            if (qq == 0) { rp_base = pp.nrd - 3; rp_mult = 0; rp_k0 = __ldg(pp.rel_table + (size_t)h * pp.nrd + pp.nrd - 1); }
+            else {
+                const int t = qq - 1, qy = t / pp.gw, qx = t % pp.gw;
+                rp_base = (qy + pp.gh - 1) * (2 * pp.gw - 1) + (qx + pp.gw - 1);
+                rp_k0 = __ldg(pp.rel_table + (size_t)h * pp.nrd + pp.nrd - 2);
+            }
+            rp_e0 = pp.nrd - 1 - rp_base;
         }
+        const uint64_t scale2 = pack2(p.scale_log2e, p.scale_log2e);
+        int xch_n = 0;
+        auto pair_max = [&](float v) {
+            float *slot = s_xch + (((xch_n & 1) * 2 + g) * 128 + row) * 2;
+            slot[hh] = v;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            const float other = slot[hh ^ 1];
+            ++xch_n;
+            return fmaxf(v, other);
+        };
+
+        for (int j = 0; j < num_kv; ++j) {
+            const bool tail = ALIGNED && j == num_main;
+            const int kbase = tail ? 0 : tok0 + j * AT_BKV;
+            const int nvalid = tail ? 1 : min(AT_BKV, ntok - j * AT_BKV);
+            const int ncols = (nvalid + 15) & ~15;
+            const int nmine = max(0, min(ncols - hh * 64, 64));          // this thread's columns of the tile (multiple of 16)
+            uint32_t r[64];
+            mbar_wait(&s_full[g], j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c * 16 < nmine) tmem_ld_32x16(tmem_S + c * 16, reinterpret_cast<uint32_t(&)[16]>(r[c * 16]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g]);                     // S(j) is in registers: the tensor core may overwrite it
+
+            // ---- u = s * scale + bias - m_run, row maximum ---------------------------------------------------------
+            float mx = -INFINITY;
+            const float neg_m = -m_run;
+            const uint64_t negm2 = pack2(neg_m, neg_m);
+            auto chunk = [&](uint32_t (&rc)[16], int c0, auto partial_tag) {      // c0: column of the tile
+                constexpr bool PARTIAL = decltype(partial_tag)::value;
+                uint64_t b2[8];
+                if (BIAS_MODE == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) b2[i] = negm2;
+                } else if (BIAS_MODE == 1) {
+                    const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
+#pragma unroll
+                    for (int gq = 0; gq < 2; ++gq) {
+                        const uint4 u = __ldg(bp + gq);
+                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { const float2 bf = __half22float2(h2[k]); b2[gq * 4 + k] = pack2(fmaf(bf.x, LOG2E, neg_m), fmaf(bf.y, LOG2E, neg_m)); }
+                    }
+                } else if (BIAS_MODE == 2) {
+                    const uint4 *kp = reinterpret_cast<const uint4 *>(s_koff + kbase + c0);
+#pragma unroll
+                    for (int gq = 0; gq < 2; ++gq) {
+                        const uint4 u = kp[gq];
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float b0 = s_tab[rp_base - rp_mult * (int)(w[k] & 0xffffu)];
+                            const float b1 = s_tab[rp_base - rp_mult * (int)(w[k] >> 16)];
+                            if (gq == 0 && k == 0 && kbase + c0 == 0) b0 = rp_k0;
+                            b2[gq * 4 + k] = add2(pack2(b0, b1), negm2);
+                        }
+                    }
+                } else {
+                    if (tail) {
+                        const float v = rp_k0 + neg_m;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) b2[i] = pack2(v, v);
+                    } else {
+                        const int e = rp_e0 + (int)s_koff[(j * AT_BKV + c0) >> 4];
+                        const uint64_t *tp = reinterpret_cast<const uint64_t *>(s_tab + e + ((e & 1) ? nrd_pad - 1 : 0));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) b2[i] = add2(tp[i], negm2);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    float t0, t1;
+                    unpack2(fma2(pack2(__uint_as_float(rc[i]), __uint_as_float(rc[i + 1])), scale2, b2[i >> 1]), t0, t1);
+                    if (PARTIAL) { t0 = (c0 + i < nvalid) ? t0 : -INFINITY; t1 = (c0 + i + 1 < nvalid) ? t1 : -INFINITY; }
+                    mx = max3(mx, t0, t1);
+                    rc[i] = __float_as_uint(t0); rc[i + 1] = __float_as_uint(t1);
+                }
+            };
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c * 16 < nmine) {
+                    const int c0 = hh * 64 + c * 16;
+                    if (c0 + 16 > nvalid) chunk(reinterpret_cast<uint32_t(&)[16]>(r[c * 16]), c0, TagTrue());
+                    else chunk(reinterpret_cast<uint32_t(&)[16]>(r[c * 16]), c0, TagFalse());
+                }
+            }
+            mx = pair_max(mx);                                   // exact maximum of the row's 128 scores, relative to m_run
+            // tile 0 fixes the reference point; later tiles move it only when a score exceeds it by 2^8 (lazy rescale)
+            const bool need = (j == 0) || (mx > 8.0f);
+            const bool any_need = __any_sync(0xffffffffu, need);
+            if (j > 0) {                                         // PV(j-1) done: P may be overwritten, O may be rescaled
+                mbar_wait(&pv_full[g], (j - 1) & 1);
+                tc_fence_after();
+            }
+            if (any_need) {
+                const float delta = need ? mx : 0.f;
+                m_run += delta;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) - delta);
+                if (j > 0) {
+                    const float alpha = ex2_approx(-delta);
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t o[16];
+                        tmem_ld_32x16(tmem_O + hh * 32 + c * 16, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x16(tmem_O + hh * 32 + c * 16, o);
+                    }
+                    if (hh == 0) {
+                        const uint32_t rs = tmem_ld_32x1(tmem_O + 64);
+                        tmem_ld_wait();
+                        tmem_st_32x1(tmem_O + 64, __float_as_uint(__uint_as_float(rs) * alpha));
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // ---- p = 2^u -> fp16 -> swizzled K-major P tile --------------------------------------------------------------
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c * 16 < nmine) {
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const __half2 h2 = __floats2half2_rn(ex2_approx(__uint_as_float(r[c * 16 + i])), ex2_approx(__uint_as_float(r[c * 16 + i + 1])));
+                        packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
+                    }
+                    *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c) << 4) ^ sw)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c + 1) << 4) ^ sw)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[g]);
+        }
+        mbar_wait(&pv_full[g], (num_kv - 1) & 1);
+        tc_fence_after();
+        {
+            uint32_t o[32];
+            tmem_ld_32x32(tmem_O + hh * 32, o);
+            const uint32_t rs = tmem_ld_32x1(tmem_O + 64);
+            tmem_ld_wait();
+            if (q_ok) {
+                const float inv = 1.0f / __uint_as_float(rs);
+                __half *dst = p.out + (size_t)(row_base + qi) * p.C + h * AT_D + hh * 32;
+#pragma unroll
+                for (int d = 0; d < AT_D / 2; d += 8) {
+                    uint4 u;
+                    __half2 *h2 = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(__uint_as_float(o[d + 2 * k]) * inv, __uint_as_float(o[d + 2 * k + 1]) * inv);
+                    *reinterpret_cast<uint4 *>(dst + d) = u;
+                }
+            }
+        }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// one cudaFuncSetAttribute per (kernel, device): the attribute is per device, the flag must be too
+struct PerDeviceFlag {
+    unsigned long long mask = 0;
+    bool test_and_set() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_ACQ_REL);
+        return (old & bit) != 0;
+    }
+};
+
+static size_t attn4_table_bytes(int mode, int nrd, int N, int num_main, int num_kv) {
+    if (mode == 3) return (size_t)2 * ((nrd + 3) & ~1) * 4 + (size_t)num_main * (AT_BKV / 16) * 2 + 16;
+    if (mode == 2) return (size_t)((nrd + 3) & ~3) * 4 + (size_t)num_kv * AT_BKV * 2 + 16;
+    return 0;
+}
+
+template <int MODE>
+static int launch_attn4(const CUtensorMap &tm, const Attn2Params &pp, cudaStream_t stream, const __half *qkv) {
+    const int ntok = pp.a.N - (MODE == 3 ? 1 : 0);
+    const int num_main = (ntok + AT_BKV - 1) / AT_BKV, num_kv = num_main + (MODE == 3 ? 1 : 0);
+    dim3 grid((ntok + 2 * AT_BQ - 1) / (2 * AT_BQ), pp.a.H, pp.a.B);
+    static int use_fwd3 = -1;     // DEPTHMAP_B200_ATTN_FWD3=1: the round-1 kernel, kept for A/B timing
+    if (use_fwd3 < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_FWD3"); use_fwd3 = (e && e[0] == '1') ? 1 : 0; }
+    if (use_fwd3 && !(MODE >= 2 && pp.nrd > 4096)) {
+        const int smem = A3_SMEM_BASE + (MODE >= 2 ? A2_TAB_BYTES : 0);
+        static PerDeviceFlag configured;
+        if (!configured.test_and_set())
+            DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attention_fwd3_kernel<MODE><<<grid, A3_THREADS, smem, stream>>>(tm, pp);
         DM_LAUNCH_CHECK("attention_fwd3_kernel");
+    } else {
+        const size_t tab = attn4_table_bytes(MODE, pp.nrd, pp.a.N, num_main, num_kv);
+        if (tab > (size_t)A4_TAB_MAX) { set_error("attention: relative-position table (%d entries) does not fit in shared memory", pp.nrd); return DM_E_UNSUPPORTED; }
+        static PerDeviceFlag configured;
+        if (!configured.test_and_set())
+            DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd4_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_MAX));
+        attention_fwd4_kernel<MODE><<<grid, A4_THREADS, A4_TAB_OFF + tab, stream>>>(tm, pp);
+        DM_LAUNCH_CHECK("attention_fwd4_kernel");
     }
     if (MODE == 3) {
         const int cls_smem = (((pp.a.N + 31) & ~31) + 256 + 64 + 8 * 64) * (int)sizeof(float);
@@ -1148,35 +985,17 @@ int attention_f16(const __half *qkv, const AttnParams &p, cudaStream_t stream, c
         set_error("attention_f16: bias row pitch must be a multiple of 8 and cover whole 128-key tiles (got %d)", p.bias_ld);
         return DM_E_INVALID;
     }
-    static int use_v1 = -1;
-    if (use_v1 < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
-    if (!use_v1 || rel_table) {
-        Attn2Params pp;
-        pp.a = p; pp.rel_table = rel_table; pp.rel_rowmax = rel_rowmax; pp.nrd = nrd; pp.gh = gh; pp.gw = gw;
-        if (rel_table) {
-            if (nrd > 4096 || p.N > 2048 || gh * gw + 1 != p.N) { set_error("attention_f16: relative-position table mode supports nrd <= 4096, N <= 2048, N = gh*gw+1"); return DM_E_UNSUPPORTED; }
-            const char *e = getenv("DEPTHMAP_B200_ATTN_GENERIC");   // read per call: the tests flip it to cover both table modes
-            const bool aligned = gw % 16 == 0 && !(e && e[0] == '1');
-            return aligned ? launch_attn2<3>(tm, pp, stream, qkv) : launch_attn2<2>(tm, pp, stream, qkv);
-        }
-        return p.bias ? launch_attn2<1>(tm, pp, stream, qkv) : launch_attn2<0>(tm, pp, stream, qkv);
+    Attn2Params pp;
+    pp.a = p; pp.rel_table = rel_table; pp.rel_rowmax = rel_rowmax; pp.nrd = nrd; pp.gh = gh; pp.gw = gw;
+    if (rel_table) {
+        if (gh * gw + 1 != p.N || nrd != (2 * gh - 1) * (2 * gw - 1) + 3) { set_error("attention_f16: relative-position mode needs N = gh*gw+1 and nrd = (2gh-1)(2gw-1)+3"); return DM_E_INVALID; }
+        const char *e = getenv("DEPTHMAP_B200_ATTN_GENERIC");   // read per call: the tests flip it to cover both table modes
+        const bool aligned = gw % 16 == 0 && !(e && e[0] == '1');
+        return aligned ? launch_attn4<3>(tm, pp, stream, qkv) : launch_attn4<2>(tm, pp, stream, qkv);
     }
-    static bool configured = false;
-    if (!configured) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-        DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-        configured = true;
-    }
-    if (p.bias && (p.bias_ld % 8 != 0 || p.bias_ld < ((p.N + AT_BKV - 1) / AT_BKV) * AT_BKV)) {
-        set_error("attention_f16: bias row pitch must be a multiple of 8 and cover whole 128-key tiles (got %d)", p.bias_ld);
-        return DM_E_INVALID;
-    }
-    dim3 grid((p.N + AT_BQ - 1) / AT_BQ, p.H, p.B);
-    if (p.bias) attention_fwd_kernel<true><<<grid, 192, AT_SMEM, stream>>>(tm, p);
-    else attention_fwd_kernel<false><<<grid, 192, AT_SMEM, stream>>>(tm, p);
-    DM_LAUNCH_CHECK("attention_fwd_kernel");
-    return DM_OK;
+    return p.bias ? launch_attn4<1>(tm, pp, stream, qkv) : launch_attn4<0>(tm, pp, stream, qkv);
 }
+
 
 }  // namespace dm
 

@@ -548,11 +548,45 @@ class DptBeitEngine(DepthAnythingV2Engine):
                 # per (head, query) maximum of the bias over all keys: the kernel's row-max upper bound
                 rowmax = torch.stack([tab[hh][idx].max(dim=1).values for hh in range(tab.shape[0])]).contiguous()
                 out.append((tab, rowmax))
-            self._bias_cache = {key: (out, new_h * new_w + 3)}  # keep one resolution resident
+            self._bias_cache = {key: (out, new_h * new_w + 3)}  # keep one resolution resident (drops dense tables too)
+        return self._bias_cache[key]
+
+    @staticmethod
+    def table_fits_on_chip(gh, gw):
+        """The table attention modes keep one head's bias table (twice, reversed, for 16-aligned grids) and the per-key
+        offsets in the 60.75 KB of shared memory the kernel has left (csrc/attention_tcgen05.cu, A4_TAB_MAX)."""
+        nrd, N = (2 * gh - 1) * (2 * gw - 1) + 3, gh * gw + 1
+        if gw % 16 == 0:
+            need = 8 * ((nrd + 3) & ~1) + 2 * ((N + 126) // 128) * 8 + 16
+        else:
+            need = 4 * ((nrd + 3) & ~3) + 2 * ((N + 127) // 128) * 128 + 16
+        return need <= 227 * 1024 - 170240
+
+    def dense_bias(self, gh, gw):
+        """Fallback for windows whose table does not fit on chip (e.g. a 3:2 image on dpt_beit_large_512: net 768x512,
+        nrd = 5988): the gather half of _get_rel_pos_bias (beit.py:52-62) done once per resolution into a dense fp16
+        [heads, N, ld] tensor per block (ld = N rounded up to whole 128-key tiles), added inside the attention kernel."""
+        import torch
+        key = ('dense', gh, gw)
+        if key not in self._bias_cache:
+            tabs, nrd = self.rel_tables(gh, gw)
+            idx = _gen_relative_position_index(gh, gw).to(self.device)
+            N = gh * gw + 1
+            ld = _ru(N, 128)
+            out = []
+            for tab, _ in tabs:
+                d = torch.zeros(tab.shape[0], N, ld, dtype=torch.float16, device=self.device)
+                d[:, :, :N] = (tab / 1.4426950408889634)[:, idx.view(-1)].view(-1, N, N).to(torch.float16)
+                out.append(d)
+            self._bias_cache[key] = (out, ld)
         return self._bias_cache[key]
 
     def attention(self, i, b, B, N, heads, C, gh, gw):
         tabs, nrd = self.rel_tables(gh, gw)
+        if not self.table_fits_on_chip(gh, gw):
+            dense, ld = self.dense_bias(gh, gw)
+            self.ops.attention(b['qkv'], B, N, heads, (C // heads) ** -0.5, b['att'], bias=dense[i], bias_ld=ld)
+            return
         self.ops.attention_relpos(b['qkv'], B, gh, gw, heads, (C // heads) ** -0.5, tabs[i][0], tabs[i][1], nrd, b['att'])
 
     def emit_feature(self, b, fi, B, N, C):
@@ -622,6 +656,8 @@ class ModelHolder:
                 if not os.path.exists(model_path):
                     raise FileNotFoundError(f"{model_path} not found (depthmap_b200 does not download checkpoints)")
                 sd = torch.load(model_path, map_location='cpu')
+                if "optimizer" in sd:       # dmidas/base_model.py:13: training checkpoints wrap the weights
+                    sd = sd["model"]
             model = DptBeitEngine(sd, name, torch.device(device))
         else:
             raise NotImplementedError(f"model_type {model_type} is not implemented in depthmap_b200 yet "
