@@ -107,7 +107,8 @@ def backbone_hooks(sd, x, cfg):
     for i in range(cfg['depth']):
         b = p + f'blocks.{i}.'
         h = F.layer_norm(t, (C,), sd[b + 'norm1.weight'].float(), sd[b + 'norm1.bias'].float(), 1e-6)
-        qkv_bias = torch.cat((sd[b + 'attn.q_bias'].float(), torch.zeros(C), sd[b + 'attn.v_bias'].float()))
+        q_bias = sd[b + 'attn.q_bias'].float()
+        qkv_bias = torch.cat((q_bias, torch.zeros_like(q_bias), sd[b + 'attn.v_bias'].float()))   # k has no bias (beit.py:70-74)
         qkv = F.linear(h, sd[b + 'attn.qkv.weight'].float(), qkv_bias)
         N = t.shape[1]
         qkv = qkv.reshape(B, N, 3, heads, -1).permute(2, 0, 3, 1, 4)

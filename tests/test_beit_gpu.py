@@ -1,14 +1,16 @@
 """GPU: MiDaS 3.1 DPT-BEiT forward on the tensor-core path vs the fp32 oracle restatement (oracle/beit_dpt.py).
 
-The oracle for this family is "parity unpinned" (timm is absent here, see the oracle header); the bar is the same as
-for DA-v2: max |d_gpu - d_ref| / (max - min of the oracle) on the raw prediction."""
+The oracle for this family is "parity unpinned" (timm is absent here, see the oracle header); the trunk is cross-checked
+against HF transformers' BeitModel, tests/test_beit_hf_crosscheck.py); the bar is the one of tests/precision.py."""
 import numpy as np
 import pytest
+
+import precision
 
 pytestmark = pytest.mark.gpu
 
 
-def _check(cuda_device, name, hw, net, B, tol_max=1e-3, tol_mean=3e-4):
+def _check(cuda_device, name, hw, net, B):
     import torch
     from depthmap_b200.depthmap_generation import DptBeitEngine
     from oracle import beit_dpt, synth_weights
@@ -19,12 +21,9 @@ def _check(cuda_device, name, hw, net, B, tol_max=1e-3, tol_mean=3e-4):
     got = eng.forward_batch(torch.from_numpy(np.stack(imgs)).to(cuda_device), net[0], net[1]).cpu().numpy()
     for i, img in enumerate(imgs):
         want, inv = beit_dpt.get_raw_prediction(img, sd, name, net[0], net[1])
-        rng = float(want.max() - want.min())
-        assert rng > 0.05
-        mx = float(np.abs(got[i] - want).max()) / rng
-        mean = float(np.abs(got[i] - want).mean()) / rng
-        print(name, hw, net, "normalised max err", mx, "mean", mean)
-        assert mx < tol_max and mean < tol_mean, (name, hw, mx, mean)
+        assert float(want.max() - want.min()) > 0.05
+        ref16 = precision.reference_fp16_error('beit', img, sd, name, net, want, cuda_device)
+        precision.check(f"{name} {hw} net {net} img{i}", got[i], want, ref16)
 
 
 @pytest.mark.parametrize("hw,net", [((64, 96), (64, 64)), ((96, 96), (96, 96)), ((80, 50), (64, 64))])

@@ -5,6 +5,8 @@ maps scaled by the oracle's (max - min); fp16 operands with fp32 accumulation / 
 import numpy as np
 import pytest
 
+import precision
+
 pytestmark = pytest.mark.gpu
 
 
@@ -27,9 +29,8 @@ def test_dav2_forward_vs_oracle(cuda_device, encoder, hw, net):
     for i, img in enumerate(imgs):
         want, inv = odav2.get_raw_prediction(img, sd, encoder, net)
         assert want.max() - want.min() > 0.1
-        mx, mean = _norm_err(got[i], want)
-        print(encoder, hw, net, "normalised max err", mx, "mean", mean)
-        assert mx < 1e-3 and mean < 3e-4, (encoder, hw, net, mx, mean)
+        ref16 = precision.reference_fp16_error('dav2', img, sd, encoder, net, want, cuda_device)
+        precision.check(f"dav2 {encoder} {hw} net {net} img{i}", got[i], want, ref16)
 
 
 def test_modelholder_api(cuda_device):
@@ -48,7 +49,7 @@ def test_modelholder_api(cuda_device):
     pred, invert = mh.get_raw_prediction(Image.fromarray(img), 56, 56)
     assert pred.dtype == np.float32 and pred.shape == (56, 84) and invert is False
     want, _ = odav2.get_raw_prediction(img, sd, 'vits', 56)
-    assert np.abs(pred - want).max() / (want.max() - want.min()) < 1e-3
+    precision.check('modelholder vits', pred, want, precision.reference_fp16_error('dav2', img, sd, 'vits', 56, want, cuda_device))
     mh.offload(); mh.reload(); mh.unload_models()
     assert mh.depth_model is None
     with pytest.raises(NotImplementedError):

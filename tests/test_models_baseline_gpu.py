@@ -3,47 +3,17 @@
   C2       dpt_beit_large_512 @512x512 at the bench batch (32) — compares images spread over the batch, because tile
            scheduling / L2 grouping of the persistent GEMMs depends on the batch
   C4 core  dpt_beit_large_384 (the ZoeDepth-NK trunk) incl. a non-square net (generic relative-position mode)
-Bar: north_star's 1e-3 on depth = max |d_gpu - d_oracle| / (max - min of the oracle), with the reference's own precision
-policy as the yardstick: the same network evaluated the way the reference runs it on a GPU (`model.half()`,
-src/depthmap_generation.py:268-275 — fp16 weights AND fp16 activations / residual stream) is measured in the same test."""
+Bar: tests/precision.py (north_star's 1e-3, with the reference's own GPU precision policy measured in the same test)."""
 import numpy as np
 import pytest
 
+import precision
+
 pytestmark = pytest.mark.gpu
-TOL_MAX, TOL_MEAN = 1e-3, 3e-4
-
-
-class _HalfView:
-    """state_dict view whose `.float()` hands back the fp16 CUDA copy: runs the oracle's functional network in the
-    reference's GPU precision (everything fp16) without touching the oracle code."""
-
-    def __init__(self, sd, dev):
-        import torch
-        self.d = {k: _HalfTensor(v.to(dev, torch.float16)) for k, v in sd.items()}
-
-    def __getitem__(self, k):
-        return self.d[k]
-
-    def get(self, k, default=None):
-        return self.d.get(k, default)
-
-
-class _HalfTensor:
-    def __init__(self, t):
-        self.t = t
-
-    def float(self):
-        return self.t
-
-
-def _err(got, want):
-    rng = float(want.max() - want.min())
-    return float(np.abs(got - want).max()) / rng, float(np.abs(got - want).mean()) / rng
 
 
 def test_dav2_vitl_518(cuda_device):
     import torch
-    import torch.nn.functional as F
     from depthmap_b200.depthmap_generation import DepthAnythingV2Engine
     from oracle import dav2 as odav2
     from oracle import synth_weights
@@ -52,18 +22,11 @@ def test_dav2_vitl_518(cuda_device):
     eng = DepthAnythingV2Engine(sd, 'vitl', cuda_device)
     imgs = [synth_rgb(518, 518, 50 + s) for s in range(3)]
     got = eng.forward_batch(torch.from_numpy(np.stack(imgs)).to(cuda_device), 518).cpu().numpy()
-    hv = _HalfView(sd, cuda_device)
     for i in (0, 2):
         want, _ = odav2.get_raw_prediction(imgs[i], sd, 'vitl', 518)
         assert want.max() - want.min() > 0.1
-        mx, mean = _err(got[i], want)
-        x, (h, w) = odav2.preprocess(imgs[i], 518)
-        with torch.no_grad():
-            ref16 = odav2.forward(hv, x.to(cuda_device, torch.float16), 'vitl').float()
-            ref16 = F.interpolate(ref16[:, None], (h, w), mode="bilinear", align_corners=True)[0, 0].cpu().numpy()
-        rmx, rmean = _err(ref16, want)
-        print(f"dav2 vitl 518 img{i}: ours max {mx:.3e} mean {mean:.3e} | reference-style fp16 max {rmx:.3e} mean {rmean:.3e}")
-        assert mx < TOL_MAX and mean < TOL_MEAN, (i, mx, mean, rmx, rmean)
+        ref16 = precision.reference_fp16_error('dav2', imgs[i], sd, 'vitl', 518, want, cuda_device)
+        precision.check(f"dav2 vitl 518 B=3 img{i}", got[i], want, ref16)
 
 
 def test_beit_large_512_batch32(cuda_device):
@@ -80,10 +43,9 @@ def test_beit_large_512_batch32(cuda_device):
     for pos in (0, 13, 31):
         k = order[pos]
         if k not in wants:
-            wants[k] = beit_dpt.get_raw_prediction(uniq[k], sd, 'beitl16_512', 512, 512)[0]
-        mx, mean = _err(got[pos], wants[k])
-        print(f"beit512 B=32 img{pos}: max {mx:.3e} mean {mean:.3e}")
-        assert mx < TOL_MAX and mean < TOL_MEAN, (pos, mx, mean)
+            w = beit_dpt.get_raw_prediction(uniq[k], sd, 'beitl16_512', 512, 512)[0]
+            wants[k] = (w, precision.reference_fp16_error('beit', uniq[k], sd, 'beitl16_512', (512, 512), w, cuda_device))
+        precision.check(f"beitl16_512 B=32 img{pos}", got[pos], wants[k][0], wants[k][1])
     # identical inputs at different batch positions give identical outputs (no dependence on tile scheduling)
     assert np.array_equal(got[0], got[3]) and np.array_equal(got[1], got[31])
 
@@ -102,6 +64,5 @@ def test_beit_large_384_and_nonsquare(cuda_device, hw, net):
     imgs = [synth_rgb(hw[0], hw[1], 90 + s) for s in range(2)]
     got = eng.forward_batch(torch.from_numpy(np.stack(imgs)).to(cuda_device), net[0], net[1]).cpu().numpy()
     want = beit_dpt.get_raw_prediction(imgs[1], sd, name, net[0], net[1])[0]
-    mx, mean = _err(got[1], want)
-    print(f"{name} {hw} net {net}: max {mx:.3e} mean {mean:.3e}")
-    assert mx < TOL_MAX and mean < TOL_MEAN, (mx, mean)
+    ref16 = precision.reference_fp16_error('beit', imgs[1], sd, name, net, want, cuda_device)
+    precision.check(f"{name} {hw} net {net}", got[1], want, ref16)
