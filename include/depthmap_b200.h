@@ -166,6 +166,41 @@ int dm_im2col_s2_f16(const void *in, int B, int H, int W, int C, void *out, void
 /* MiDaS ProjectReadout input: out[b*(N-1)+p, :] = [x[b,1+p,:], x[b,0,:]] (fp32 -> fp16), x fp32 [B, N, C] */
 int dm_concat_readout_f16(const float *x, int B, int N, int C, void *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * D7 — ZoeDepth-NK on top of the DPT-BEiT core (csrc/zoe_kernels.cu).   replaces
+ *   dzoedepth/models/depth_model.py:57-152 (pad + flip test-time augmentation), base_models/midas.py:175-186 (PrepForMidas),
+ *   zoedepth_nk/zoedepth_nk_v1.py:159-243 (router, seed bins, attractors, conditional log-binomial),
+ *   layers/attractor.py:127-208, layers/dist_layers.py:29-121, layers/patch_transformer.py:29-92.
+ * Forward index f = 2*b + flip: image b and its horizontal flip go through the network as one batch of 2B forwards.
+ * `logits` is fp32 [F, lld]: columns 0 / 1 are the router's nyu / kitti logits of that forward; every head kernel picks
+ * the routed head itself (argmax, first index on ties, as torch.argmax) — no host synchronisation.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* uint8 RGB [B,H,W,3] -> /255 -> reflect pad (pad_h, pad_w) -> flip for odd f -> bilinear align_corners=True resize to
+ * net_h x net_w -> (x - 0.5) / 0.5 -> fp16 patch matrix [2B * gh * gw, kpad], kpad = 3*patch^2 */
+int dm_zoe_preprocess_patchify(const uint8_t *rgb, int B, int H, int W, int pad_h, int pad_w, int net_h, int net_w, int patch, void *out,
+                               int kpad, void *stream);
+/* x = LayerNorm(x) in place (fp32 [rows, 128]) + fp16 copy: post-norm nn.TransformerEncoderLayer of the router */
+int dm_layernorm_post_f16(float *x, long long rows, int C, const float *gamma, const float *beta, float eps, void *out, void *stream);
+/* self-attention of the router: qkv fp16 [F*S, 3*heads*32] (q | k | v) -> out fp16 [F*S, heads*32] */
+int dm_attention_small_f16(const void *qkv, int F, int S, int heads, float scale, void *out, void *stream);
+int dm_cast_f32_f16(const float *x, long long n, void *out, void *stream);
+/* out[r, 0..63] = softplus(seed[r, head*64 .. head*64+63]) for the routed head of row r's forward */
+int dm_zoe_select_softplus(const float *seed, int ld, const float *logits, int lld, int F, int rows_per_fwd, float *out, void *stream);
+/* out = a + bilinear_align_corners(b_small -> H x W); NHWC fp16 */
+int dm_resize_add_nhwc_f16(const void *a, const void *b_small, int B, int Hs, int Ws, int C, void *out, int H, int W, void *stream);
+/* AttractorLayerUnnormed (inverse attractor, mean of 16): A fp32 [F*H*W, lda] pre-softplus, routed head's 16 columns at
+ * head*32; b_prev fp32 [F,Hp,Wp,64] is resized (bilinear, align_corners) to H x W; b_out fp32 [F,H,W,64] */
+int dm_zoe_attractor(const float *A, int lda, const float *logits, int lld, const float *b_prev, int F, int Hp, int Wp, int H, int W,
+                     float *b_out, void *stream);
+/* ConditionalLogBinomial + expectation over the 64 bin centres, per net pixel.  o32: relu'd out_conv activation fp16
+ * [F,nh,nw,ldo] (32 channels used); ze fp32 [F,h3,w3,ldz] = W_e . b_emb (head at column head*64, 40 used); bc fp32
+ * [F,h3,w3,64] bin centres; wo [2][32][40], b0 [2][40], w2 [2][4][40], b2 [2][4] fp32 device arrays; out fp32 [F,nh,nw] */
+int dm_zoe_clb_final(const void *o32, int ldo, const float *ze, int ldz, const float *bc, const float *logits, int lld, const float *wo,
+                     const float *b0, const float *w2, const float *b2, int F, int nh, int nw, int h3, int w3, float min_temp, float max_temp,
+                     float *out, void *stream);
+/* out[b] = mean(crop(bicubic(d[2b])), unflip(crop(bicubic(d[2b+1])))): d fp32 [2B,nh,nw] -> out fp32 [B,H,W] */
+int dm_zoe_tta_combine(const float *d, int B, int nh, int nw, int pad_h, int pad_w, int H, int W, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,7 +140,7 @@ def make_beit_dpt_state_dict(name='beit_tiny', seed=0, dtype=torch.float32):
     return sd
 
 
-def make_zoedepth_head_state_dict(feat_ch=256, out_conv_ch=32, seed=0, dtype=torch.float32):
+def make_zoedepth_head_state_dict(feat_ch=256, out_conv_ch=32, seed=0, dtype=torch.float32, gain=1.0):
     """Seeded ZoeDepth-NK metric-head weights in the checkpoint layout of dzoedepth/models/zoedepth_nk/zoedepth_nk_v1.py
     (keys as `ZoeDepthNK.state_dict()` minus "core."): 64 bins, 128-d bin embedding, 16 attractors per level (the count the
     reference really instantiates, see oracle/zoedepth.py), 4-layer / 4-head / 1024-ffn router."""
@@ -152,8 +152,10 @@ def make_zoedepth_head_state_dict(feat_ch=256, out_conv_ch=32, seed=0, dtype=tor
     sd = {}
 
     def conv(key, cout, cin):
-        sd[key + ".weight"] = w(cout, cin, 1, 1)
-        sd[key + ".bias"] = w(cout, s=0.02)
+        # gain > 1: fan-in scaled weights times `gain`, so that bin centres, attractor points and the log-binomial
+        # parameters really vary over the image (the 0.05-std default gives an almost constant depth map)
+        sd[key + ".weight"] = w(cout, cin, 1, 1) if gain == 1.0 else w(cout, cin, 1, 1, s=gain * cin ** -0.5)
+        sd[key + ".bias"] = w(cout, s=0.02 if gain == 1.0 else 0.3)
 
     def lin(key, cout, cin):
         sd[key + ".weight"] = w(cout, cin)

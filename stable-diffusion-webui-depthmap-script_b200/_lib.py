@@ -62,6 +62,8 @@ EXPORTS = [
     "dm_normalmap_workspace_bytes", "dm_normalmap",
     "dm_gemm_ex", "dm_conv3x3_ex", "dm_gemm_f16", "dm_conv3x3_f16", "dm_attention_f16", "dm_attention_relpos_f16", "dm_preprocess_patchify",
     "dm_assemble_tokens", "dm_layernorm_f16", "dm_resize_bilinear_nhwc_f16", "dm_resize_f32", "dm_im2col_s2_f16", "dm_concat_readout_f16",
+    "dm_zoe_preprocess_patchify", "dm_layernorm_post_f16", "dm_attention_small_f16", "dm_cast_f32_f16", "dm_zoe_select_softplus",
+    "dm_resize_add_nhwc_f16", "dm_zoe_attractor", "dm_zoe_clb_final", "dm_zoe_tta_combine",
 ]
 
 
@@ -118,6 +120,16 @@ def _bind_optional(L):
         L.dm_resize_f32.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp]
         L.dm_im2col_s2_f16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
         L.dm_concat_readout_f16.argtypes = [vp, i32, i32, i32, vp, vp]
+    if hasattr(L, "dm_zoe_clb_final"):
+        L.dm_zoe_preprocess_patchify.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
+        L.dm_layernorm_post_f16.argtypes = [vp, c.c_longlong, i32, vp, vp, f32, vp, vp]
+        L.dm_attention_small_f16.argtypes = [vp, i32, i32, i32, f32, vp, vp]
+        L.dm_cast_f32_f16.argtypes = [vp, c.c_longlong, vp, vp]
+        L.dm_zoe_select_softplus.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
+        L.dm_resize_add_nhwc_f16.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]
+        L.dm_zoe_attractor.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]
+        L.dm_zoe_clb_final.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp]
+        L.dm_zoe_tta_combine.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
 
 
 def check(rc: int, what: str = ""):

@@ -926,18 +926,6 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// one cudaFuncSetAttribute per (kernel, device): the attribute is per device, the flag must be too
-struct PerDeviceFlag {
-    unsigned long long mask = 0;
-    bool test_and_set() {
-        int d = 0;
-        cudaGetDevice(&d);
-        const unsigned long long bit = 1ull << (d & 63);
-        const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_ACQ_REL);
-        return (old & bit) != 0;
-    }
-};
-
 static size_t attn4_table_bytes(int mode, int nrd, int N, int num_main, int num_kv) {
     if (mode == 3) return (size_t)2 * ((nrd + 3) & ~1) * 4 + (size_t)num_main * (AT_BKV / 16) * 2 + 16;
     if (mode == 2) return (size_t)((nrd + 3) & ~3) * 4 + (size_t)num_kv * AT_BKV * 2 + 16;

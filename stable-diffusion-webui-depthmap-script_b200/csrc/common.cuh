@@ -26,6 +26,19 @@ int cuda_fail(cudaError_t e, const char *what);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// "have I configured this kernel on the current device yet?"  cudaFuncSetAttribute is per device, so the flag is a bit per
+// device ordinal, set atomically (a process-wide bool skipped the call on the second GPU of a process).
+struct PerDeviceFlag {
+    unsigned long long mask = 0;
+    bool test_and_set() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_ACQ_REL);
+        return (old & bit) != 0;
+    }
+};
+
 // order-preserving float <-> uint32 maps so min/max reductions can use integer atomics
 __device__ __forceinline__ uint32_t f32_to_ordered(float f) {
     uint32_t u = __float_as_uint(f);

@@ -950,11 +950,9 @@ int make_tmap_nhwc(CUtensorMap *tm, const void *ptr, uint64_t B, uint64_t H, uin
 template <int BN, bool CONV>
 static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.test_and_set())
         DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
     dim3 grid(m_tiles, (p.N + BN - 1) / BN);
     gemm_tcgen05_kernel<BN, CONV><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     DM_LAUNCH_CHECK("gemm_tcgen05_kernel");
@@ -998,11 +996,9 @@ static int epilogue_spec(const GemmParams &p, bool conv) {
 
 template <bool CONV, int SPEC>
 static int launch_persist_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.test_and_set())
         DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_persist_kernel<CONV, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfg::SMEM_BYTES));
-        configured = true;
-    }
     const int n_tiles = p.N / PersistCfg::BN;
     const int tiles = m_tiles * n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -1024,11 +1020,9 @@ static int launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 
 template <bool CONV, int SPEC>
 static int launch_2sm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int m_tiles, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.test_and_set())
         DM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel<CONV, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::SMEM_BYTES));
-        configured = true;
-    }
     const int m_pairs = (m_tiles + 1) / 2;
     const int n_tiles = p.N / PairCfg::BN;
     const int tiles = m_pairs * n_tiles;

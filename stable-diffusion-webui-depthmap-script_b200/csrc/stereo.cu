@@ -586,11 +586,12 @@ extern "C" __attribute__((visibility("default"))) int dm_stereo(const uint8_t *r
         set_error("dm_stereo: a %d px row needs %zu B of shared memory (> 227 KB); image too wide for this fill mode", W, smem);
         return DM_E_UNSUPPORTED;
     }
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(stereo_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        DM_CUDA_CHECK(cudaFuncSetAttribute(stereo_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = 227 * 1024;
+    if (smem > 48 * 1024) {
+        static PerDeviceFlag configured;
+        if (!configured.test_and_set()) {
+            DM_CUDA_CHECK(cudaFuncSetAttribute(stereo_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+            DM_CUDA_CHECK(cudaFuncSetAttribute(stereo_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        }
     }
     if (p->depth_kind == DM_DEPTH_U16) {
         const int64_t n = (int64_t)H * W;

@@ -349,9 +349,21 @@ class DepthAnythingV2Engine:
         gh, gw = nh // P_, nw // P_
         Np, N = gh * gw, gh * gw + 1
         b = self._buffers(B, nh, nw)
-        E, A = _lib, _lib
-        # image2tensor + patch embedding + tokens
+        # image2tensor
         ops.patchify(rgb, B, H, W, nh, nw, P_, self.MEAN, self.STD, self.CHAN_MAP, b['patches'], self.kpad)
+        self.run_network(b, B, nh, nw)
+        return self.run_head(b, B, H, W, nh, nw, out_hw)
+
+    def run_network(self, b, B, nh, nw):
+        """patch embedding -> transformer blocks -> reassemble -> fusion blocks; leaves refinenet1's output in b['path'][3]
+        (and layer4_rn / refinenet4..2 in b['l'][3] / b['path'][0..2], which the ZoeDepth head reads)."""
+        ops, w, cfg = self.ops, self.w, self.cfg
+        C, heads, Fp = cfg['embed_dim'], cfg['heads'], self.Fp
+        P_ = self.PATCH
+        gh, gw = nh // P_, nw // P_
+        Np, N = gh * gw, gh * gw + 1
+        E, A = _lib, _lib
+        # patch embedding + tokens
         ops.gemm(b['patches'], self.kpad, w['pe_w'], self.kpad, B * Np, C, self.kpad, bias=w['pe_b'], C=b['pe'], ldc=C)
         ops.tokens(b['pe'], w['cls'], self._pos(gh, gw) if self._pos_embed is not None else None, b['x'], B, Np, C)
         rows = B * N
@@ -407,7 +419,14 @@ class DepthAnythingV2Engine:
             t = up[step + 1]
             ops.gemm(b[f'u{li}'], Fp, w[f'rf{rf}_out_w'], Fp, B * s[0] * s[1], Fp, Fp, bias=w[f'rf{rf}_out_b'], C=b['v'][step + 1], ldc=Fp)
             ops.resize_nhwc(b['v'][step + 1], B, s[0], s[1], Fp, b['path'][step + 1], t[0], t[1])
-        t = up[3]
+
+    def run_head(self, b, B, H, W, nh, nw, out_hw=None):
+        """output_conv (dpt.py:139-150 / dpt_depth.py:150-158) + the final resize to the image size."""
+        import torch
+        ops, w = self.ops, self.w
+        Fp = self.Fp
+        E, A = _lib, _lib
+        t = b['up_sizes'][3]
         ops.conv3x3(b['path'][3], B, t[0], t[1], Fp, w['oc1_w'], self.F2p, bias=w['oc1_b'], C=b['oc1'])
         ops.resize_nhwc(b['oc1'], B, t[0], t[1], self.F2p, b['oc1u'], nh, nw)
         # conv3x3 -> ReLU -> conv1x1 -> ReLU (+ the outer F.relu, idempotent) fused into one epilogue
@@ -597,6 +616,241 @@ class DptBeitEngine(DepthAnythingV2Engine):
         self.ops.gemm(b['cat'], 2 * C, rw, 2 * C, B * (N - 1), C, 2 * C, act=_lib.ACT_GELU, bias=rb, C=b['feat'][fi], ldc=C)
 
 
+ZOE_CONFIG = dict(n_bins=64, emb=128, min_temp=0.0212, max_temp=50.0, router_dim=128, router_heads=4, router_layers=4)
+
+
+class ZoeDepthNKEngine(DptBeitEngine):
+    """ZoeDepth-NK (model types 7-9 share this head family; 9 = zoedepth_nk) on the sm_100a kernels: DepthModel.infer_pil
+    (pad + flip test-time augmentation, dzoedepth/models/depth_model.py:57-152), PrepForMidas (base_models/midas.py:175-186),
+    the DPT-BEiT-L-384 core with MidasCore's hooks (midas.py:258-319) and the metric head of ZoeDepthNK.forward
+    (zoedepth_nk/zoedepth_nk_v1.py:159-243).  Image b and its horizontal flip run as forwards 2b / 2b+1 of ONE batch; the
+    router picks nyu / kitti per forward on the device (argmax of two logits, no host sync, no cross-image vote).
+    Checkpoint layout: MiDaS weights under "core.core.", head weights at the top level."""
+
+    def __init__(self, state_dict, device, core_name='beitl16_384'):
+        core_sd = {k[len("core.core."):]: v for k, v in state_dict.items() if k.startswith("core.core.")}
+        self._head_sd = {k: v for k, v in state_dict.items() if not k.startswith("core.")}
+        super().__init__(core_sd, core_name, device)
+        self._pack_head(self._head_sd)
+        self._zbuf_key, self._zbufs = None, {}
+
+    # ---- weights -------------------------------------------------------------------------------------------------------
+    def _pack_head(self, sd):
+        import torch
+        dev = self.device
+        z = {}
+
+        def W(key, rows=None, cols=None):      # 1x1 conv / linear weight -> fp16 [rows, cols] (zero padded)
+            t = sd[key + '.weight'].detach().to(dev).float()
+            t = t.reshape(t.shape[0], -1)
+            r, c = rows or t.shape[0], cols or t.shape[1]
+            o = torch.zeros(r, c, dtype=torch.float16, device=dev)
+            o[:t.shape[0], :t.shape[1]] = t.to(torch.float16)
+            return o
+
+        def Bv(key, n=None):
+            t = sd[key + '.bias'].detach().to(dev).float().reshape(-1)
+            o = torch.zeros(n or t.numel(), dtype=torch.float32, device=dev)
+            o[:t.numel()] = t
+            return o
+
+        z['conv2'] = (W('conv2'), Bv('conv2'))
+        z['emb'] = (W('patch_transformer.embedding_convPxP'), Bv('patch_transformer.embedding_convPxP'))
+        layers = []
+        for i in range(ZOE_CONFIG['router_layers']):
+            q = f'patch_transformer.transformer_encoder.layers.{i}'
+            f32 = lambda k: sd[k].detach().to(dev).float().contiguous()
+            layers.append(dict(
+                in_w=sd[q + '.self_attn.in_proj_weight'].detach().to(dev, torch.float16).contiguous(), in_b=f32(q + '.self_attn.in_proj_bias'),
+                out=(W(q + '.self_attn.out_proj'), Bv(q + '.self_attn.out_proj')),
+                l1=(W(q + '.linear1'), Bv(q + '.linear1')), l2=(W(q + '.linear2'), Bv(q + '.linear2')),
+                n1=(f32(q + '.norm1.weight'), f32(q + '.norm1.bias')), n2=(f32(q + '.norm2.weight'), f32(q + '.norm2.bias'))))
+        z['layers'] = layers
+        z['cls0'] = (W('mlp_classifier.0'), Bv('mlp_classifier.0'))
+        z['cls2'] = (W('mlp_classifier.2', rows=32), Bv('mlp_classifier.2', 32))
+        z['ones128'] = torch.ones(128, dtype=torch.float32, device=dev)
+        z['zeros128'] = torch.zeros(128, dtype=torch.float32, device=dev)
+        names = ('nyu', 'kitti')
+        # seed bin regressors of both heads side by side: net.0 stacked, net.2 block-diagonal (nyu -> columns 0..63, kitti 64..127)
+        z['seed0'] = (torch.cat([W(f'seed_bin_regressors.{n}._net.0') for n in names]), torch.cat([Bv(f'seed_bin_regressors.{n}._net.0') for n in names]))
+        w2 = torch.zeros(128, 128, dtype=torch.float16, device=dev)
+        for k, n in enumerate(names):
+            w2[64 * k:64 * k + 64, 64 * k:64 * k + 64] = W(f'seed_bin_regressors.{n}._net.2')
+        z['seed2'] = (w2, torch.cat([Bv(f'seed_bin_regressors.{n}._net.2') for n in names]))
+        z['sproj'] = ((W('seed_projector._net.0'), Bv('seed_projector._net.0')), (W('seed_projector._net.2'), Bv('seed_projector._net.2')))
+        z['proj'] = [((W(f'projectors.{i}._net.0'), Bv(f'projectors.{i}._net.0')), (W(f'projectors.{i}._net.2'), Bv(f'projectors.{i}._net.2'))) for i in range(4)]
+        att = []
+        for i in range(4):
+            a0 = (torch.cat([W(f'attractors.{n}.{i}._net.0') for n in names]), torch.cat([Bv(f'attractors.{n}.{i}._net.0') for n in names]))
+            w2 = torch.zeros(64, 256, dtype=torch.float16, device=dev)
+            b2 = torch.zeros(64, dtype=torch.float32, device=dev)
+            for k, n in enumerate(names):
+                t = W(f'attractors.{n}.{i}._net.2')
+                if t.shape[0] != 16:
+                    raise NotImplementedError("ZoeDepth-NK attractor layers with other than 16 attractors (the reference always builds 16)")
+                w2[32 * k:32 * k + 16, 128 * k:128 * k + 128] = t
+                b2[32 * k:32 * k + 16] = Bv(f'attractors.{n}.{i}._net.2')
+            att.append((a0, (w2, b2)))
+        z['att'] = att
+        # conditional log-binomial: mlp.0 split into its out_conv part (32 inputs, evaluated per pixel in clb_final) and its bin
+        # embedding part (128 inputs, a GEMM before the up-sampling: a 1x1 conv commutes with bilinear interpolation)
+        we = torch.zeros(128, 128, dtype=torch.float16, device=dev)
+        wo = torch.zeros(2, 32, 40, dtype=torch.float32, device=dev)
+        b0 = torch.zeros(2, 40, dtype=torch.float32, device=dev)
+        w2c = torch.zeros(2, 4, 40, dtype=torch.float32, device=dev)
+        b2c = torch.zeros(2, 4, dtype=torch.float32, device=dev)
+        for k, n in enumerate(names):
+            m0 = sd[f'conditional_log_binomial.{n}.mlp.0.weight'].detach().to(dev).float().reshape(40, 160)
+            wo[k] = m0[:, :32].t()
+            we[64 * k:64 * k + 40] = m0[:, 32:].to(torch.float16)
+            b0[k] = sd[f'conditional_log_binomial.{n}.mlp.0.bias'].detach().to(dev).float()
+            w2c[k] = sd[f'conditional_log_binomial.{n}.mlp.2.weight'].detach().to(dev).float().reshape(4, 40)
+            b2c[k] = sd[f'conditional_log_binomial.{n}.mlp.2.bias'].detach().to(dev).float()
+        z['clb'] = (we, wo.contiguous(), b0.contiguous(), w2c.contiguous(), b2c.contiguous())
+        # out_conv with 64 output channels (32 real + 32 zero) so the stored activation is a valid GEMM-friendly NHWC tensor
+        h = 'depth_head.'
+        z['oc2_w64'] = _conv_w(self._oc2_weight.to(dev), self.F2p, 64)
+        z['oc2_b64'] = _pad_vec(self._oc2_bias.to(dev), 64)
+        self.z = z
+        self._pe_cache = {}
+
+    def _pack(self, sd):
+        self._oc2_weight = sd['scratch.output_conv.2.weight'].detach()
+        self._oc2_bias = sd['scratch.output_conv.2.bias'].detach()
+        super()._pack(sd)
+
+    def _router_pe(self, S):
+        """PositionalEncodingPermute1D replacement of patch_transformer.py:45-62: sin | cos of position * 10000^(-2i/E)."""
+        import torch
+        if S not in self._pe_cache:
+            E = ZOE_CONFIG['router_dim']
+            pos = torch.arange(0, S, dtype=torch.float32, device=self.device).unsqueeze(1)
+            idx = torch.arange(0, E, 2, dtype=torch.float32, device=self.device).unsqueeze(0)
+            div = torch.exp(idx * (-torch.log(torch.tensor(10000.0, device=self.device)) / E))
+            pe = pos * div
+            self._pe_cache = {S: torch.cat([torch.sin(pe), torch.cos(pe)], dim=1).contiguous()}
+        return self._pe_cache[S]
+
+    def _zbuffers(self, F, nh, nw, b):
+        import torch
+        key = (F, nh, nw)
+        if self._zbuf_key == key:
+            return self._zbufs
+        dev = self.device
+        h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        s3 = b['sizes'][3]
+        n0 = s3[0] * s3[1]
+        S = n0 + 1
+        levels = list(b['up_sizes'])                       # (h, w) of refinenet4..1 outputs
+        zb = dict(x16=h16(F * n0, self.Fp), emb=h16(F * n0, 128), X=f32(F * S, 128), h=h16(F * S, 128), qkv=h16(F * S, 384), att=h16(F * S, 128),
+                  ff=h16(F * S, 1024), c1=h16(F, 128), logits=f32(F, 32), s0=h16(F * n0, 128), seed=f32(F * n0, 128), bprev=f32(F * n0, 64),
+                  p0=h16(F * n0, 64), pemb=h16(F * n0, 128), S=S, n0=n0, levels=levels)
+        zb['t'] = [h16(F * h * w, 64) for h, w in levels]
+        zb['bemb'] = [h16(F * h * w, 128) for h, w in levels]
+        zb['xin'] = [h16(F * h * w, 128) for h, w in levels]
+        zb['a0'] = [h16(F * h * w, 256) for h, w in levels]
+        zb['A'] = [f32(F * h * w, 64) for h, w in levels]
+        zb['bnew'] = [f32(F * h * w, 64) for h, w in levels]
+        zb['ze'] = f32(F * levels[3][0] * levels[3][1], 128)
+        zb['o32'] = h16(F, nh, nw, 64)
+        zb['d'] = f32(F, nh, nw)
+        self._zbufs, self._zbuf_key = zb, key
+        return zb
+
+    # ---- forward -------------------------------------------------------------------------------------------------------
+    def forward_batch(self, rgb, net_w, net_h=None, out_hw=None):
+        """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] metric depth (what estimatezoedepth returns; invert = True)."""
+        import torch
+        L = self.ops.L
+        ops, z = self.ops, self.z
+        st = _lib.stream_ptr
+        B, H, W, _ = rgb.shape
+        net_h = net_h if net_h is not None else net_w
+        pad_h, pad_w = int(np.sqrt(H / 2) * 3.0), int(np.sqrt(W / 2) * 3.0)       # depth_model.py:80-82 (fh = fw = 3)
+        Hp, Wp = H + 2 * pad_h, W + 2 * pad_w
+        nw, nh = midas_net_size(Wp, Hp, net_w, net_h)                               # PrepForMidas: keep aspect, x32, "minimal"
+        F = 2 * B
+        b = self._buffers(F, nh, nw)
+        _lib.check(L.dm_zoe_preprocess_patchify(rgb.data_ptr(), B, H, W, pad_h, pad_w, nh, nw, self.PATCH, b['patches'].data_ptr(), self.kpad, st()),
+                   "dm_zoe_preprocess_patchify")
+        ops.launches += 1
+        self.run_network(b, F, nh, nw)
+        zb = self._zbuffers(F, nh, nw, b)
+        Fp = self.Fp
+        E_, A_ = _lib, _lib
+        # out_conv activation (MidasCore hooks output_conv[3], the 32-channel ReLU)
+        t = b['up_sizes'][3]
+        ops.conv3x3(b['path'][3], F, t[0], t[1], Fp, self.w['oc1_w'], self.F2p, bias=self.w['oc1_b'], C=b['oc1'])
+        ops.resize_nhwc(b['oc1'], F, t[0], t[1], self.F2p, b['oc1u'], nh, nw)
+        ops.conv3x3(b['oc1u'], F, nh, nw, self.F2p, z['oc2_w64'], 64, act=A_.ACT_RELU, bias=z['oc2_b64'], C=zb['o32'])
+        n0, S = zb['n0'], zb['S']
+        s3 = b['sizes'][3]
+
+        def lin(a, lda, wb, M, N, K, out=None, ldc=None, act=A_.ACT_NONE, f32out=None, resid=None):
+            wt, bias = wb
+            if resid is not None:
+                ops.gemm(a, lda, wt, K, M, N, K, epi=E_.EPI_RESID_F32, bias=bias, X=resid, ldx=N, gamma=z['ones128'])
+            elif f32out is not None:
+                ops.gemm(a, lda, wt, K, M, N, K, epi=E_.EPI_STORE_F32, act=act, bias=bias, X=f32out, ldx=N)
+            else:
+                ops.gemm(a, lda, wt, K, M, N, K, act=act, bias=bias, C=out, ldc=ldc or N)
+
+        # x = conv2(bottleneck) (zoedepth_nk_v1.py:176-178)
+        lin(b['l'][3], Fp, z['conv2'], F * n0, Fp, Fp, out=zb['x16'])
+        # ---- router: PatchTransformerEncoder (patch size 1) + MLP classifier (:186-195) ----
+        lin(zb['x16'], Fp, z['emb'], F * n0, 128, Fp, out=zb['emb'])
+        ops.tokens(zb['emb'], z['zeros128'], self._router_pe(S), zb['X'], F, n0, 128)
+        _lib.check(L.dm_cast_f32_f16(zb['X'].data_ptr(), F * S * 128, zb['h'].data_ptr(), st()), "dm_cast_f32_f16")
+        ops.launches += 1
+        for lay in z['layers']:
+            lin(zb['h'], 128, (lay['in_w'], lay['in_b']), F * S, 384, 128, out=zb['qkv'])
+            _lib.check(L.dm_attention_small_f16(zb['qkv'].data_ptr(), F, S, ZOE_CONFIG['router_heads'], 1.0 / math.sqrt(32.0), zb['att'].data_ptr(), st()),
+                       "dm_attention_small_f16")
+            lin(zb['att'], 128, lay['out'], F * S, 128, 128, resid=zb['X'])
+            _lib.check(L.dm_layernorm_post_f16(zb['X'].data_ptr(), F * S, 128, lay['n1'][0].data_ptr(), lay['n1'][1].data_ptr(), 1e-5, zb['h'].data_ptr(), st()),
+                       "dm_layernorm_post_f16")
+            lin(zb['h'], 128, lay['l1'], F * S, 1024, 128, out=zb['ff'], act=A_.ACT_RELU)
+            lin(zb['ff'], 1024, lay['l2'], F * S, 128, 1024, resid=zb['X'])
+            _lib.check(L.dm_layernorm_post_f16(zb['X'].data_ptr(), F * S, 128, lay['n2'][0].data_ptr(), lay['n2'][1].data_ptr(), 1e-5, zb['h'].data_ptr(), st()),
+                       "dm_layernorm_post_f16")
+            ops.launches += 3
+        lin(zb['h'], S * 128, z['cls0'], F, 128, 128, out=zb['c1'], act=A_.ACT_RELU)       # token 0 of every forward (row pitch S*128)
+        lin(zb['c1'], 128, z['cls2'], F, 32, 128, f32out=zb['logits'])
+        lg = zb['logits']
+        # ---- seed bins + seed embedding (:197-206) ----
+        lin(zb['x16'], Fp, z['seed0'], F * n0, 128, Fp, out=zb['s0'], act=A_.ACT_RELU)
+        lin(zb['s0'], 128, z['seed2'], F * n0, 128, 128, f32out=zb['seed'])
+        _lib.check(L.dm_zoe_select_softplus(zb['seed'].data_ptr(), 128, lg.data_ptr(), 32, F, n0, zb['bprev'].data_ptr(), st()), "dm_zoe_select_softplus")
+        lin(zb['x16'], Fp, z['sproj'][0], F * n0, 64, Fp, out=zb['p0'], act=A_.ACT_RELU)
+        lin(zb['p0'], 64, z['sproj'][1], F * n0, 128, 64, out=zb['pemb'])
+        ops.launches += 1
+        # ---- attractor levels (:207-214) ----
+        bprev, pemb, (hp, wp) = zb['bprev'], zb['pemb'], s3
+        for i, (h, w) in enumerate(zb['levels']):
+            M = F * h * w
+            lin(b['path'][i], Fp, z['proj'][i][0], M, 64, Fp, out=zb['t'][i], act=A_.ACT_RELU)
+            lin(zb['t'][i], 64, z['proj'][i][1], M, 128, 64, out=zb['bemb'][i])
+            _lib.check(L.dm_resize_add_nhwc_f16(zb['bemb'][i].data_ptr(), pemb.data_ptr(), F, hp, wp, 128, zb['xin'][i].data_ptr(), h, w, st()),
+                       "dm_resize_add_nhwc_f16")
+            lin(zb['xin'][i], 128, z['att'][i][0], M, 256, 128, out=zb['a0'][i], act=A_.ACT_RELU)
+            lin(zb['a0'][i], 256, z['att'][i][1], M, 64, 256, f32out=zb['A'][i])
+            _lib.check(L.dm_zoe_attractor(zb['A'][i].data_ptr(), 64, lg.data_ptr(), 32, bprev.data_ptr(), F, hp, wp, h, w, zb['bnew'][i].data_ptr(), st()),
+                       "dm_zoe_attractor")
+            ops.launches += 2
+            bprev, pemb, (hp, wp) = zb['bnew'][i], zb['bemb'][i], (h, w)
+        # ---- conditional log-binomial + expectation (:216-236), then un-pad / un-flip / average (depth_model.py:88-129) ----
+        we, wo, b0, w2c, b2c = z['clb']
+        ops.gemm(zb['bemb'][3], 128, we, 128, F * hp * wp, 128, 128, epi=E_.EPI_STORE_F32, X=zb['ze'], ldx=128)
+        _lib.check(L.dm_zoe_clb_final(zb['o32'].data_ptr(), 64, zb['ze'].data_ptr(), 128, bprev.data_ptr(), lg.data_ptr(), 32, wo.data_ptr(), b0.data_ptr(),
+                                      w2c.data_ptr(), b2c.data_ptr(), F, nh, nw, hp, wp, ZOE_CONFIG['min_temp'], ZOE_CONFIG['max_temp'],
+                                      zb['d'].data_ptr(), st()), "dm_zoe_clb_final")
+        out = torch.empty(B, H, W, dtype=torch.float32, device=self.device)
+        _lib.check(L.dm_zoe_tta_combine(zb['d'].data_ptr(), B, nh, nw, pad_h, pad_w, H, W, out.data_ptr(), st()), "dm_zoe_tta_combine")
+        ops.launches += 2
+        return out
+
+
 class ModelHolder:
     """Same public surface as the reference's ModelHolder (src/depthmap_generation.py:40-403)."""
 
@@ -659,9 +913,20 @@ class ModelHolder:
                 if "optimizer" in sd:       # dmidas/base_model.py:13: training checkpoints wrap the weights
                     sd = sd["model"]
             model = DptBeitEngine(sd, name, torch.device(device))
+        elif model_type == 9:  # zoedepth_nk (src/depthmap_generation.py:221-226: ZoeD_M12_NK.pt)
+            if self.weights_provider is not None:
+                sd = self.weights_provider(model_type)
+            else:
+                model_path = "./models/zoedepth/ZoeD_M12_NK.pt"
+                if not os.path.exists(model_path):
+                    raise FileNotFoundError(f"{model_path} not found (depthmap_b200 does not download checkpoints)")
+                sd = torch.load(model_path, map_location='cpu')
+                if "model" in sd:           # dzoedepth/models/model_io.py:52-53
+                    sd = sd["model"]
+            model = ZoeDepthNKEngine(sd, torch.device(device))
         else:
             raise NotImplementedError(f"model_type {model_type} is not implemented in depthmap_b200 yet "
-                                      f"(implemented: 1, 2 = DPT-BEiT-L 512/384; 12, 13, 14 = Depth-Anything-V2 S/B/L)")
+                                      f"(implemented: 1, 2 = DPT-BEiT-L 512/384; 9 = ZoeDepth-NK; 12, 13, 14 = Depth-Anything-V2 S/B/L)")
         self.depth_model = model
         self.depth_model_type = model_type
         self.resize_mode = "minimal"
@@ -709,7 +974,7 @@ class ModelHolder:
         """uint8 CUDA [B,H,W,3] -> (float32 CUDA [B,H,W], invert flag).  Batched form of get_raw_prediction."""
         if self.depth_model is None:
             raise RuntimeError("no depth model loaded; call ensure_models first")
-        if self.depth_model_type in (1, 2, 12, 13, 14):
+        if self.depth_model_type in (1, 2, 9, 12, 13, 14):
             pred = self.depth_model.forward_batch(rgb, net_width, net_height)
         else:
             raise NotImplementedError(f"model_type {self.depth_model_type}")

@@ -39,18 +39,25 @@ def test_beit_large_512_batch32(cuda_device):
     uniq = [synth_rgb(512, 512, 70 + s) for s in range(3)]
     order = [0, 1, 2] * 10 + [1, 2]                        # 32 images, three distinct ones spread over the batch
     got = eng.forward_batch(torch.from_numpy(np.stack([uniq[k] for k in order])).to(cuda_device), 512, 512).cpu().numpy()
-    wants = {}
+    # a batch of one gives bit-identical results: no reduction order depends on the batch size or on the tile schedule
+    solo = eng.forward_batch(torch.from_numpy(uniq[0][None]).to(cuda_device), 512, 512).cpu().numpy()[0]
+    print("[precision] beitl16_512 B=32 vs B=1, image 0: max abs diff", float(np.abs(solo - got[0]).max()))
+    wants, failures = {}, []
     for pos in (0, 13, 31):
         k = order[pos]
         if k not in wants:
             w = beit_dpt.get_raw_prediction(uniq[k], sd, 'beitl16_512', 512, 512)[0]
             wants[k] = (w, precision.reference_fp16_error('beit', uniq[k], sd, 'beitl16_512', (512, 512), w, cuda_device))
-        precision.check(f"beitl16_512 B=32 img{pos}", got[pos], wants[k][0], wants[k][1])
-    # identical inputs at different batch positions give identical outputs (no dependence on tile scheduling)
+        try:
+            precision.check(f"beitl16_512 B=32 img{pos}", got[pos], wants[k][0], wants[k][1])
+        except AssertionError as e:
+            failures.append(str(e))
+    assert np.array_equal(solo, got[0])
+    # identical inputs at different batch positions give identical outputs
     assert np.array_equal(got[0], got[3]) and np.array_equal(got[1], got[31])
+    assert not failures, failures
 
 
-@pytest.mark.parametrize("hw,net", [((384, 384), (384, 384)), ((384, 512), (384, 384)), ((512, 768), (512, 512))])
 def test_beit_large_384_and_nonsquare(cuda_device, hw, net):
     """beitl16_384 at its native size, on a 4:3 image (net 512x384: generic relative-position mode, window 24 -> 24x32)
     and — ADVICE r1 — beitl16_512 on a 3:2 image (net 768x512, nrd = 5988 > 4096)."""
