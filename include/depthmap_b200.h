@@ -147,7 +147,8 @@ int dm_attention_f16(const void *qkv, int B, int N, int H, float scale, const vo
  * fp32 [H, nrd] = the per-head bias table already resized to the gh x gw window, multiplied by log2(e);
  * nrd = (2gh-1)(2gw-1)+3, N = gh*gw+1 tokens (class token first); rel_rowmax_log2e is fp32 [H, N] = max over keys of the
  * bias of each query (same scaling), a setup-time constant that gives the online softmax its row-max upper bound.
- * No [H,N,N] bias tensor is read by the kernel. */
+ * No [H,N,N] bias tensor is read by the kernel.  rel_rowmax_log2e may be NULL (only the round-1 kernel, selected with
+ * DEPTHMAP_B200_ATTN_FWD3=1, uses it). */
 int dm_attention_relpos_f16(const void *qkv, int B, int gh, int gw, int H, float scale, const float *rel_table_log2e,
                             const float *rel_rowmax_log2e, int nrd, void *out, void *stream);
 /* uint8 RGB [B,H,W,3] -> (cv2-style bicubic resize to net_h x net_w) -> (x/255 - mean)/std -> fp16 patch matrix
@@ -200,6 +201,57 @@ int dm_zoe_clb_final(const void *o32, int ldo, const float *ze, int ldz, const f
                      float *out, void *stream);
 /* out[b] = mean(crop(bicubic(d[2b])), unflip(crop(bicubic(d[2b+1])))): d fp32 [2B,nh,nw] -> out fp32 [B,H,W] */
 int dm_zoe_tta_combine(const float *d, int B, int nh, int nw, int pad_h, int pad_w, int H, int W, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * §8(f) rank 1 — video mode's cross-frame normalisation.    replaces  src/video_mode.py:103-128 (process_predicitons)
+ * Frames are fp32 [count, hw] device arrays.  Each step is its own call so that, when the frames of a clip are sharded
+ * over GPUs, the host can put the (tiny) collective between two steps: all-reduce MIN/MAX of lohi[2] after
+ * dm_video_minmax; all-reduce SUM of the int32[1024] histograms at byte offset 32 of `workspace` between
+ * dm_video_select_hist and dm_video_select_pick.  Bit-exact with numpy (float32 for 'none', float64 for 'experimental').
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t dm_video_workspace_bytes(void);
+/* 5-tap temporal blend; `frames` holds global frames [base_global, base_global+count), out gets blended [out_first, +out_count) */
+int dm_video_blend(const float *frames, long long hw, int base_global, int count, int n_total, int out_first, int out_count, float *out,
+                   void *stream);
+int dm_video_minmax(const float *x, long long n, float *lohi_out, void *workspace, size_t workspace_bytes, void *stream);
+int dm_video_scale_f32(const float *x, long long n, const float *lohi, float *out, void *stream);
+int dm_video_select_init(void *workspace, const long long ranks[4], void *stream);
+int dm_video_select_hist(const float *x, long long n, int pass, void *workspace, void *stream);
+int dm_video_select_pick(void *workspace, int pass, void *stream);
+int dm_video_select_bounds(const void *workspace, double gamma_lo, double gamma_hi, double *ab_out, void *stream);
+int dm_video_scale_f64(const float *x, long long n, const double *ab, double *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * §8(b) — model-level entry points (csrc/model.cu): a handle that owns the packed checkpoint, the activation buffers, the
+ * resolution-dependent tables and one captured CUDA graph per shape; a forward is ONE call.
+ *   replaces  the network part of ModelHolder.load_models / get_raw_prediction (src/depthmap_generation.py:76-301,375-403)
+ *             for model types 1, 2 (MiDaS 3.1 DPT-BEiT-L 512 / 384) and 12, 13, 14 (Depth-Anything-V2 S / B / L).
+ * dm_weight: one tensor of the upstream checkpoint (state_dict key, HOST pointer, dtype 0 = fp32 / 1 = fp16 / 2 = bf16, shape);
+ * the blob is only read during dm_model_create.  dtype of the model: 0 = fp16 operands, fp32 accumulation (the only one).
+ * dm_depth_forward: rgb uint8 [B,H,W,3] (device) -> depth_out fp32 [B,out_h,out_w] (device), asynchronous on `stream`; the net
+ * size follows the reference's Resize rule for the family from (net_w, net_h) (dm_model_net_size).  The first call of a
+ * shape allocates and runs eagerly, the second captures a CUDA graph, later calls replay it (DEPTHMAP_B200_MODEL_GRAPH=0
+ * disables); inside an outer stream capture the launches are simply recorded into that capture.
+ * Thread-compatible: one handle per thread; handles are independent.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct dm_weight {
+    const char *name;
+    const void *data_host;
+    int32_t dtype;
+    int32_t ndim;
+    int64_t shape[4];
+} dm_weight;
+typedef struct dm_weight_blob {
+    const dm_weight *items;
+    int32_t count;
+} dm_weight_blob;
+typedef struct dm_model dm_model_t;
+int dm_model_create(dm_model_t **out, int model_type, const dm_weight_blob *weights, int device, int dtype);
+int dm_model_destroy(dm_model_t *model);
+int dm_model_net_size(const dm_model_t *model, int W, int H, int net_w, int net_h, int *nw_out, int *nh_out);
+long long dm_model_launches(const dm_model_t *model);
+int dm_depth_forward(dm_model_t *model, const uint8_t *rgb, int B, int H, int W, int net_w, int net_h, float *depth_out, int out_h, int out_w,
+                     void *stream);
 
 #ifdef __cplusplus
 }

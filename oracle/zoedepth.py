@@ -67,7 +67,7 @@ def router_logits(x_d0, sd):
     emb = _conv1x1(x_d0, sd, "patch_transformer.embedding_convPxP").flatten(2)      # patch size 1
     emb = F.pad(emb, (1, 0)).permute(2, 0, 1)                                       # zero "class token" first; [S, N, E]
     S, N, E = emb.shape
-    emb = emb + _positional_encoding_1d(S, E, emb.device).unsqueeze(1)
+    emb = emb + _positional_encoding_1d(S, E, emb.device).unsqueeze(1).to(emb.dtype)
     for i in range(CONFIG["router_layers"]):
         emb = _encoder_layer(emb, sd, f"patch_transformer.transformer_encoder.layers.{i}", CONFIG["router_heads"])
     e0 = emb[0]

@@ -31,6 +31,16 @@ class StereoParams(ctypes.Structure):
     ]
 
 
+class Weight(ctypes.Structure):
+    """mirror of dm_weight"""
+    _fields_ = [("name", ctypes.c_char_p), ("data_host", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("ndim", ctypes.c_int32),
+                ("shape", ctypes.c_int64 * 4)]
+
+
+class WeightBlob(ctypes.Structure):
+    _fields_ = [("items", ctypes.POINTER(Weight)), ("count", ctypes.c_int32)]
+
+
 class GemmDesc(ctypes.Structure):
     """mirror of dm_gemm_desc (include/depthmap_b200.h)"""
     _fields_ = [
@@ -64,6 +74,9 @@ EXPORTS = [
     "dm_assemble_tokens", "dm_layernorm_f16", "dm_resize_bilinear_nhwc_f16", "dm_resize_f32", "dm_im2col_s2_f16", "dm_concat_readout_f16",
     "dm_zoe_preprocess_patchify", "dm_layernorm_post_f16", "dm_attention_small_f16", "dm_cast_f32_f16", "dm_zoe_select_softplus",
     "dm_resize_add_nhwc_f16", "dm_zoe_attractor", "dm_zoe_clb_final", "dm_zoe_tta_combine",
+    "dm_video_workspace_bytes", "dm_video_blend", "dm_video_minmax", "dm_video_scale_f32", "dm_video_select_init", "dm_video_select_hist",
+    "dm_video_select_pick", "dm_video_select_bounds", "dm_video_scale_f64",
+    "dm_model_create", "dm_model_destroy", "dm_model_net_size", "dm_model_launches", "dm_depth_forward",
 ]
 
 
@@ -94,6 +107,24 @@ def load() -> ctypes.CDLL:
         L.dm_normalmap_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
         L.dm_normalmap_workspace_bytes.restype = sz
         L.dm_normalmap.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+        if hasattr(L, "dm_video_blend"):
+            ll, dbl = c.c_longlong, c.c_double
+            L.dm_video_workspace_bytes.restype = sz
+            L.dm_video_blend.argtypes = [vp, ll, i32, i32, i32, i32, i32, vp, vp]
+            L.dm_video_minmax.argtypes = [vp, ll, vp, vp, sz, vp]
+            L.dm_video_scale_f32.argtypes = [vp, ll, vp, vp, vp]
+            L.dm_video_select_init.argtypes = [vp, c.POINTER(ll), vp]
+            L.dm_video_select_hist.argtypes = [vp, ll, i32, vp, vp]
+            L.dm_video_select_pick.argtypes = [vp, i32, vp]
+            L.dm_video_select_bounds.argtypes = [vp, dbl, dbl, vp, vp]
+            L.dm_video_scale_f64.argtypes = [vp, ll, vp, vp, vp]
+        if hasattr(L, "dm_model_create"):
+            L.dm_model_create.argtypes = [c.POINTER(vp), i32, c.POINTER(WeightBlob), i32, i32]
+            L.dm_model_destroy.argtypes = [vp]
+            L.dm_model_net_size.argtypes = [vp, i32, i32, i32, i32, c.POINTER(i32), c.POINTER(i32)]
+            L.dm_model_launches.argtypes = [vp]
+            L.dm_model_launches.restype = c.c_longlong
+            L.dm_depth_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp]
         _bind_optional(L)
         _lib = L
         return L

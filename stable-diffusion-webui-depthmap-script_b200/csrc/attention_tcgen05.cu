@@ -598,6 +598,8 @@ __device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__host__ __device__ __forceinline__ int attn4_nrd_pad(int nrd) { return ((nrd + 1 + 15) & ~31) + 16 >= nrd + 1 ? ((nrd + 1 + 15) & ~31) + 16 : ((nrd + 1 + 15) & ~31) + 48; }
+
 template <int BIAS_MODE>
 __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, Attn2Params pp) {
     const AttnParams &p = pp.a;
@@ -611,7 +613,9 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 17);
     float *s_xch = reinterpret_cast<float *>(smem_raw + A4_XCH_OFF);
     float *s_tab = reinterpret_cast<float *>(smem_raw + A4_TAB_OFF);
-    const int nrd_pad = (pp.nrd + 3) & ~1;                    // even, >= nrd + 1: start of the shifted copy (mode 3)
+    // start of the shifted copy (mode 3): even, >= nrd + 1, and 16 banks away from copy 0 (the even lanes of a half-warp read
+    // copy 0, the odd lanes copy 1, 16 consecutive words each: with the copies 16 (mod 32) words apart they never share a bank)
+    const int nrd_pad = attn4_nrd_pad(pp.nrd);
     uint16_t *s_koff = reinterpret_cast<uint16_t *>(s_tab + (ALIGNED ? 2 * nrd_pad : ((pp.nrd + 3) & ~3)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -778,9 +782,14 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
             uint32_t r[64];
             mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
+            if (nmine == 64) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c * 16 < nmine) tmem_ld_32x16(tmem_S + c * 16, reinterpret_cast<uint32_t(&)[16]>(r[c * 16]));
+                for (int c = 0; c < 4; ++c) tmem_ld_32x16(tmem_S + c * 16, reinterpret_cast<uint32_t(&)[16]>(r[c * 16]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c * 16 < nmine) tmem_ld_32x16(tmem_S + c * 16, reinterpret_cast<uint32_t(&)[16]>(r[c * 16]));
+            }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -790,7 +799,9 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
             float mx = -INFINITY;
             const float neg_m = -m_run;
             const uint64_t negm2 = pack2(neg_m, neg_m);
-            auto chunk = [&](uint32_t (&rc)[16], int c0, auto partial_tag) {      // c0: column of the tile
+            uint32_t koff4[2] = {0u, 0u};                         // mode 3: the four 16-key chunk offsets of this thread's 64 columns
+            if (BIAS_MODE == 3 && !tail) { const uint2 kk = *reinterpret_cast<const uint2 *>(s_koff + j * 8 + hh * 4); koff4[0] = kk.x; koff4[1] = kk.y; }
+            auto chunk = [&](uint32_t (&rc)[16], int c, int c0, auto partial_tag) {      // c: chunk of this thread, c0: column of the tile
                 constexpr bool PARTIAL = decltype(partial_tag)::value;
                 uint64_t b2[8];
                 if (BIAS_MODE == 0) {
@@ -825,7 +836,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
 #pragma unroll
                         for (int i = 0; i < 8; ++i) b2[i] = pack2(v, v);
                     } else {
-                        const int e = rp_e0 + (int)s_koff[(j * AT_BKV + c0) >> 4];
+                        const int e = rp_e0 + (int)((koff4[c >> 1] >> ((c & 1) * 16)) & 0xffffu);
                         const uint64_t *tp = reinterpret_cast<const uint64_t *>(s_tab + e + ((e & 1) ? nrd_pad - 1 : 0));
 #pragma unroll
                         for (int i = 0; i < 8; ++i) b2[i] = add2(tp[i], negm2);
@@ -840,12 +851,18 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                     rc[i] = __float_as_uint(t0); rc[i + 1] = __float_as_uint(t1);
                 }
             };
+            const bool full = nvalid == AT_BKV;                   // every main tile but a ragged last one: no per-chunk branches
+            if (full) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c * 16 < nmine) {
-                    const int c0 = hh * 64 + c * 16;
-                    if (c0 + 16 > nvalid) chunk(reinterpret_cast<uint32_t(&)[16]>(r[c * 16]), c0, TagTrue());
-                    else chunk(reinterpret_cast<uint32_t(&)[16]>(r[c * 16]), c0, TagFalse());
+                for (int c = 0; c < 4; ++c) chunk(reinterpret_cast<uint32_t(&)[16]>(r[c * 16]), c, hh * 64 + c * 16, TagFalse());
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 16 < nmine) {
+                        const int c0 = hh * 64 + c * 16;
+                        if (c0 + 16 > nvalid) chunk(reinterpret_cast<uint32_t(&)[16]>(r[c * 16]), c, c0, TagTrue());
+                        else chunk(reinterpret_cast<uint32_t(&)[16]>(r[c * 16]), c, c0, TagFalse());
+                    }
                 }
             }
             mx = pair_max(mx);                                   // exact maximum of the row's 128 scores, relative to m_run
@@ -881,18 +898,23 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                 }
             }
             // ---- p = 2^u -> fp16 -> swizzled K-major P tile --------------------------------------------------------------
+            auto emit = [&](int c) {
+                uint32_t packed[8];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c * 16 < nmine) {
-                    uint32_t packed[8];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const __half2 h2 = __floats2half2_rn(ex2_approx(__uint_as_float(r[c * 16 + i])), ex2_approx(__uint_as_float(r[c * 16 + i + 1])));
-                        packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
-                    }
-                    *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c) << 4) ^ sw)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c + 1) << 4) ^ sw)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                for (int i = 0; i < 16; i += 2) {
+                    const __half2 h2 = __floats2half2_rn(ex2_approx(__uint_as_float(r[c * 16 + i])), ex2_approx(__uint_as_float(r[c * 16 + i + 1])));
+                    packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
                 }
+                *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c) << 4) ^ sw)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c + 1) << 4) ^ sw)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            };
+            if (nmine == 64) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) emit(c);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c * 16 < nmine) emit(c);
             }
             fence_proxy_async();
             tc_fence_before();
@@ -927,7 +949,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
 }
 
 static size_t attn4_table_bytes(int mode, int nrd, int N, int num_main, int num_kv) {
-    if (mode == 3) return (size_t)2 * ((nrd + 3) & ~1) * 4 + (size_t)num_main * (AT_BKV / 16) * 2 + 16;
+    if (mode == 3) return (size_t)2 * attn4_nrd_pad(nrd) * 4 + (size_t)(num_main * (AT_BKV / 16) + 8) * 2 + 16;
     if (mode == 2) return (size_t)((nrd + 3) & ~3) * 4 + (size_t)num_kv * AT_BKV * 2 + 16;
     return 0;
 }
@@ -939,7 +961,7 @@ static int launch_attn4(const CUtensorMap &tm, const Attn2Params &pp, cudaStream
     dim3 grid((ntok + 2 * AT_BQ - 1) / (2 * AT_BQ), pp.a.H, pp.a.B);
     static int use_fwd3 = -1;     // DEPTHMAP_B200_ATTN_FWD3=1: the round-1 kernel, kept for A/B timing
     if (use_fwd3 < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_FWD3"); use_fwd3 = (e && e[0] == '1') ? 1 : 0; }
-    if (use_fwd3 && !(MODE >= 2 && pp.nrd > 4096)) {
+    if (use_fwd3 && !(MODE >= 2 && (pp.nrd > 4096 || !pp.rel_rowmax))) {
         const int smem = A3_SMEM_BASE + (MODE >= 2 ? A2_TAB_BYTES : 0);
         static PerDeviceFlag configured;
         if (!configured.test_and_set())
@@ -1005,6 +1027,6 @@ extern "C" __attribute__((visibility("default"))) int dm_attention_relpos_f16(co
     p.scale_log2e = scale * 1.4426950408889634f;
     p.bias = nullptr; p.bias_ld = 0;
     p.out = (__half *)out;
-    if (!rel_table_log2e || !rel_rowmax_log2e) { dm::set_error("dm_attention_relpos_f16: table / rowmax is NULL"); return DM_E_INVALID; }
+    if (!rel_table_log2e) { dm::set_error("dm_attention_relpos_f16: table is NULL"); return DM_E_INVALID; }
     return dm::attention_f16((const __half *)qkv, p, (cudaStream_t)stream, rel_table_log2e, rel_rowmax_log2e, nrd, gh, gw);
 }

@@ -316,3 +316,142 @@ extern "C" __attribute__((visibility("default"))) int dm_normalize_u16_outliers(
     DM_LAUNCH_CHECK("quantize_outliers_kernel");
     return DM_OK;
 }
+
+// =====================================================================================================================
+// §8(f) rank 1 — video mode's cross-frame normalisation.  Replaces src/video_mode.py:103-128 (process_predicitons).
+//   'none'          every frame scaled with the GLOBAL float32 min / max over all frames: one min/max reduction (an
+//                   all-reduce(MIN/MAX) of two floats when the frames are sharded over GPUs) + one scaling pass;
+//   'experimental'  the 0.5 / 99.5 percentiles of a 5-tap temporal blend (0.1 0.2 0.4 0.2 0.1, frame indices clamped) give
+//                   the bounds; the ORIGINAL frames are scaled in float64, unclipped.  The percentiles are found with the
+//                   exact radix select above run over the whole blended stack; when frames are sharded, the four
+//                   256-bin histograms of a pass are summed across ranks (an all-reduce of 4 KB) before the digit pick.
+// Every step is its own entry point so the host can put the collective between them; nothing synchronises with the host.
+// =====================================================================================================================
+namespace dm {
+
+__global__ void __launch_bounds__(256) video_blend_kernel(const float *__restrict__ frames, int64_t hw, int base_global, int n_total,
+                                                          int out_first, int out_count, float *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)out_count * hw) return;
+    const int i = (int)(idx / hw);
+    const int64_t px = idx - (int64_t)i * hw;
+    const int g = out_first + i;
+    const float taps[5] = {0.10f, 0.20f, 0.40f, 0.20f, 0.10f};       // float32(mul) * float32 frame, accumulated in float32
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+        int k = g + u - 2;
+        k = k < 0 ? 0 : (k > n_total - 1 ? n_total - 1 : k);
+        acc = __fadd_rn(acc, __fmul_rn(taps[u], __ldg(frames + (int64_t)(k - base_global) * hw + px)));
+    }
+    out[idx] = acc;
+}
+
+__global__ void video_minmax_export_kernel(const uint32_t *ws, float *out2) {
+    if (threadIdx.x == 0) { out2[0] = ordered_to_f32(ws[0]); out2[1] = ordered_to_f32(ws[1]); }
+}
+
+__global__ void __launch_bounds__(256) video_scale_f32_kernel(const float *__restrict__ x, int64_t n, const float *__restrict__ lohi, float *__restrict__ out) {
+    const float lo = lohi[0], den = __fsub_rn(lohi[1], lohi[0]);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) out[i] = __fdiv_rn(__fsub_rn(__ldg(x + i), lo), den);
+}
+
+__global__ void video_bounds_kernel(const SelectState *st, double gamma_lo, double gamma_hi, double *ab) {
+    if (threadIdx.x != 0) return;
+    auto lerp = [](float a, float bb, double t) {     // numpy _lerp, as in quantize_outliers_kernel
+        const double diff = (double)__fsub_rn(bb, a);
+        return t >= 0.5 ? __dsub_rn((double)bb, __dmul_rn(diff, __dsub_rn(1.0, t))) : __dadd_rn((double)a, __dmul_rn(diff, t));
+    };
+    ab[0] = lerp(ordered_to_f32(st->prefix[0]), ordered_to_f32(st->prefix[1]), gamma_lo);
+    ab[1] = lerp(ordered_to_f32(st->prefix[2]), ordered_to_f32(st->prefix[3]), gamma_hi);
+}
+
+__global__ void __launch_bounds__(256) video_scale_f64_kernel(const float *__restrict__ x, int64_t n, const double *__restrict__ ab, double *__restrict__ out) {
+    const double a = ab[0], den = __dsub_rn(ab[1], ab[0]);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) out[i] = __ddiv_rn(__dsub_rn((double)__ldg(x + i), a), den);
+}
+
+static int video_grid(int64_t n) {
+    int64_t b = (n + 256 * 8 - 1) / (256 * 8);
+    return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+
+}  // namespace dm
+
+#define DM_EXPORT extern "C" __attribute__((visibility("default")))
+
+DM_EXPORT size_t dm_video_workspace_bytes(void) { return dm::align_up(sizeof(dm::SelectState), 256) + 256; }
+
+/* frames: fp32 [count, hw] = global frames [base_global, base_global + count); out: blended global frames [out_first, out_first + out_count) */
+DM_EXPORT int dm_video_blend(const float *frames, long long hw, int base_global, int count, int n_total, int out_first, int out_count, float *out, void *stream_) {
+    using namespace dm;
+    if (!frames || !out || hw <= 0 || count <= 0 || n_total <= 0 || out_count <= 0) { set_error("dm_video_blend: bad arguments"); return DM_E_INVALID; }
+    const int lo = out_first - 2 < 0 ? 0 : out_first - 2, hi = out_first + out_count + 1 > n_total - 1 ? n_total - 1 : out_first + out_count + 1;
+    if (lo < base_global || hi > base_global + count - 1) { set_error("dm_video_blend: the local frames do not cover the two-frame halo"); return DM_E_INVALID; }
+    const int64_t total = (int64_t)out_count * hw;
+    video_blend_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(frames, hw, base_global, n_total, out_first, out_count, out);
+    DM_LAUNCH_CHECK("video_blend_kernel");
+    return DM_OK;
+}
+
+/* exact float32 min / max of x[0..n) -> lohi_out[2] (device) */
+DM_EXPORT int dm_video_minmax(const float *x, long long n, float *lohi_out, void *workspace, size_t workspace_bytes, void *stream_) {
+    using namespace dm;
+    if (!x || !lohi_out || n <= 0 || !workspace || workspace_bytes < dm_video_workspace_bytes()) { set_error("dm_video_minmax: bad arguments"); return DM_E_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    uint32_t *ws = (uint32_t *)((uint8_t *)workspace + align_up(sizeof(SelectState), 256));
+    const int vec_ok = (n % 4 == 0) && (((uintptr_t)x) % 16 == 0);
+    minmax_init_kernel<<<1, 256, 0, stream>>>(ws, 1);
+    minmax_f32_kernel<<<dim3(video_grid(vec_ok ? n / 4 : n), 1), 256, 0, stream>>>(x, n, ws, vec_ok);
+    video_minmax_export_kernel<<<1, 32, 0, stream>>>(ws, lohi_out);
+    DM_LAUNCH_CHECK("video_minmax");
+    return DM_OK;
+}
+
+DM_EXPORT int dm_video_scale_f32(const float *x, long long n, const float *lohi, float *out, void *stream_) {
+    using namespace dm;
+    video_scale_f32_kernel<<<video_grid(n), 256, 0, (cudaStream_t)stream_>>>(x, n, lohi, out);
+    DM_LAUNCH_CHECK("video_scale_f32_kernel");
+    return DM_OK;
+}
+
+/* radix select over a (possibly sharded) stack: init once, then for pass = 0..3: hist (local) -> [sum the histograms over ranks:
+ * int32[1024] at byte offset 32 of the workspace] -> pick.  ranks[4] are GLOBAL 0-based order-statistic ranks. */
+DM_EXPORT int dm_video_select_init(void *workspace, const long long ranks[4], void *stream_) {
+    using namespace dm;
+    for (int i = 0; i < 4; ++i) if (ranks[i] < 0 || ranks[i] >= (1ll << 31)) { set_error("dm_video_select_init: rank out of range (stack must hold < 2^31 values)"); return DM_E_INVALID; }
+    select_init_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>((SelectState *)workspace, 1, (uint32_t)ranks[0], (uint32_t)ranks[1], (uint32_t)ranks[2], (uint32_t)ranks[3]);
+    DM_LAUNCH_CHECK("select_init_kernel");
+    return DM_OK;
+}
+DM_EXPORT int dm_video_select_hist(const float *x, long long n, int pass, void *workspace, void *stream_) {
+    using namespace dm;
+    if (n > 0) {
+        int sx = (int)((n + 256 * 16 - 1) / (256 * 16));
+        sx = sx < 1 ? 1 : (sx > 148 * 4 ? 148 * 4 : sx);
+        select_hist_kernel<<<dim3(sx, 1), 256, 0, (cudaStream_t)stream_>>>(x, n, 0, pass, (SelectState *)workspace);
+        DM_LAUNCH_CHECK("select_hist_kernel");
+    }
+    return DM_OK;
+}
+DM_EXPORT int dm_video_select_pick(void *workspace, int pass, void *stream_) {
+    using namespace dm;
+    select_pick_kernel<<<1, 128, 0, (cudaStream_t)stream_>>>((SelectState *)workspace, pass);
+    DM_LAUNCH_CHECK("select_pick_kernel");
+    return DM_OK;
+}
+/* np.percentile's float64 interpolation of the selected order statistics -> ab_out[2] (device doubles) */
+DM_EXPORT int dm_video_select_bounds(const void *workspace, double gamma_lo, double gamma_hi, double *ab_out, void *stream_) {
+    using namespace dm;
+    video_bounds_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((const SelectState *)workspace, gamma_lo, gamma_hi, ab_out);
+    DM_LAUNCH_CHECK("video_bounds_kernel");
+    return DM_OK;
+}
+DM_EXPORT int dm_video_scale_f64(const float *x, long long n, const double *ab, double *out, void *stream_) {
+    using namespace dm;
+    video_scale_f64_kernel<<<video_grid(n), 256, 0, (cudaStream_t)stream_>>>(x, n, ab, out);
+    DM_LAUNCH_CHECK("video_scale_f64_kernel");
+    return DM_OK;
+}

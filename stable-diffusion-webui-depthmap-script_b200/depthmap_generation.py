@@ -576,7 +576,8 @@ class DptBeitEngine(DepthAnythingV2Engine):
         offsets in the 60.75 KB of shared memory the kernel has left (csrc/attention_tcgen05.cu, A4_TAB_MAX)."""
         nrd, N = (2 * gh - 1) * (2 * gw - 1) + 3, gh * gw + 1
         if gw % 16 == 0:
-            need = 8 * ((nrd + 3) & ~1) + 2 * ((N + 126) // 128) * 8 + 16
+            nrd_pad = ((nrd + 16) & ~31) + 16                 # csrc/attention_tcgen05.cu: attn4_nrd_pad
+            need = 8 * nrd_pad + 2 * (((N + 126) // 128) * 8 + 8) + 16
         else:
             need = 4 * ((nrd + 3) & ~3) + 2 * ((N + 127) // 128) * 128 + 16
         return need <= 227 * 1024 - 170240
@@ -614,6 +615,87 @@ class DptBeitEngine(DepthAnythingV2Engine):
         _lib.check(self.ops.L.dm_concat_readout_f16(b['x'].data_ptr(), B, N, C, b['cat'].data_ptr(), _lib.stream_ptr()), "dm_concat_readout_f16")
         self.ops.launches += 1
         self.ops.gemm(b['cat'], 2 * C, rw, 2 * C, B * (N - 1), C, 2 * C, act=_lib.ACT_GELU, bias=rb, C=b['feat'][fi], ldc=C)
+
+
+class NativeDepthModel:
+    """Thin caller of the model-level C-ABI (include/depthmap_b200.h: dm_model_create / dm_depth_forward / dm_model_destroy,
+    csrc/model.cu): the handle owns the packed weights, the activation buffers, the resolution tables and a captured CUDA
+    graph per shape; a forward is one C call.  Model types 1, 2 (DPT-BEiT-L 512 / 384) and 12, 13, 14 (Depth-Anything-V2)."""
+
+    _DT = {"torch.float32": 0, "torch.float16": 1, "torch.bfloat16": 2}
+
+    def __init__(self, state_dict, model_type, device):
+        import torch
+        self.L = _lib.load()
+        if not hasattr(self.L, "dm_model_create"):
+            raise RuntimeError("depthmap_b200: native library lacks dm_model_create; rebuild csrc (no fallback exists)")
+        self.device = torch.device(device)
+        self.model_type = model_type
+        keep, items = [], []
+        for name, t in state_dict.items():
+            if not torch.is_tensor(t) or not t.is_floating_point():
+                continue
+            t = t.detach().to("cpu")
+            if str(t.dtype) not in self._DT:
+                t = t.float()
+            t = t.contiguous()
+            keep.append(t)
+            w = _lib.Weight()
+            w.name = name.encode()
+            w.data_host = t.data_ptr()
+            w.dtype = self._DT[str(t.dtype)]
+            w.ndim = min(t.dim(), 4)
+            shape = list(t.shape) if t.dim() <= 4 else [int(t.numel())]
+            if t.dim() > 4:
+                w.ndim = 1
+            for k in range(4):
+                w.shape[k] = shape[k] if k < len(shape) else 1
+            items.append(w)
+        arr = (_lib.Weight * len(items))(*items)
+        blob = _lib.WeightBlob(arr, len(items))
+        h = ctypes.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(self.L.dm_model_create(ctypes.byref(h), int(model_type), ctypes.byref(blob), int(idx), 0), "dm_model_create")
+        self.handle = h
+        del keep
+
+    def net_size(self, W, H, net_w, net_h):
+        nw, nh = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.L.dm_model_net_size(self.handle, W, H, net_w, net_h, ctypes.byref(nw), ctypes.byref(nh)), "dm_model_net_size")
+        return nw.value, nh.value
+
+    @property
+    def launches(self):
+        return int(self.L.dm_model_launches(self.handle))
+
+    def forward_batch(self, rgb, net_w, net_h=None, out_hw=None):
+        """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] raw prediction."""
+        import torch
+        if self.handle is None:
+            raise RuntimeError("model was destroyed")
+        if rgb.dtype != torch.uint8 or rgb.dim() != 4 or rgb.shape[-1] != 3:
+            raise ValueError("rgb must be a uint8 tensor [B,H,W,3]")
+        rgb = rgb.contiguous()
+        B, H, W, _ = rgb.shape
+        oh, ow = out_hw if out_hw is not None else (H, W)
+        out = torch.empty(B, oh, ow, dtype=torch.float32, device=rgb.device)
+        _lib.check(self.L.dm_depth_forward(self.handle, rgb.data_ptr(), B, H, W, int(net_w), int(net_h if net_h is not None else net_w),
+                                           out.data_ptr(), oh, ow, _lib.stream_ptr()), "dm_depth_forward")
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None) is not None:
+            self.L.dm_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def to(self, device):
+        return self
 
 
 ZOE_CONFIG = dict(n_bins=64, emb=128, min_temp=0.0212, max_temp=50.0, router_dim=128, router_heads=4, router_layers=4)
@@ -900,7 +982,7 @@ class ModelHolder:
                 if not os.path.exists(model_path):
                     raise FileNotFoundError(f"{model_path} not found (depthmap_b200 does not download checkpoints)")
                 sd = torch.load(model_path, map_location='cpu')
-            model = DepthAnythingV2Engine(sd, f'vit{letter}', torch.device(device))
+            model = NativeDepthModel(sd, model_type, torch.device(device))
         elif model_type in (1, 2):  # dpt_beit_large_512 / dpt_beit_large_384 (MiDaS 3.1)
             name = {1: 'beitl16_512', 2: 'beitl16_384'}[model_type]
             if self.weights_provider is not None:
@@ -912,7 +994,7 @@ class ModelHolder:
                 sd = torch.load(model_path, map_location='cpu')
                 if "optimizer" in sd:       # dmidas/base_model.py:13: training checkpoints wrap the weights
                     sd = sd["model"]
-            model = DptBeitEngine(sd, name, torch.device(device))
+            model = NativeDepthModel(sd, model_type, torch.device(device))
         elif model_type == 9:  # zoedepth_nk (src/depthmap_generation.py:221-226: ZoeD_M12_NK.pt)
             if self.weights_provider is not None:
                 sd = self.weights_provider(model_type)
@@ -958,6 +1040,8 @@ class ModelHolder:
 
     def unload_models(self):
         if self.depth_model is not None or self.pix2pix_model is not None:
+            if hasattr(self.depth_model, "close"):
+                self.depth_model.close()
             self.depth_model = None
             self.pix2pix_model = None
             gc.collect()

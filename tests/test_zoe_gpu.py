@@ -34,7 +34,8 @@ def test_zoedepth_tiny_core_vs_oracle(cuda_device, seed, hw, net):
     for i, img in enumerate(imgs):
         want, invert = ozd.get_raw_prediction(img, sd, net[0], net[1], core_name='beit_tiny')
         assert invert is True and want.max() - want.min() > 0.05
-        precision.check(f"zoedepth_nk tiny seed{seed} {hw} net {net} img{i}", got[i], want)
+        ref16 = precision.reference_fp16_error_zoe(img, sd, net[0], net[1], 'beit_tiny', want, cuda_device)
+        precision.check(f"zoedepth_nk tiny seed{seed} {hw} net {net} img{i}", got[i], want, ref16)
 
 
 def test_zoedepth_nk_beit384_core(cuda_device):
@@ -53,5 +54,6 @@ def test_zoedepth_nk_beit384_core(cuda_device):
     pred, invert = mh.get_raw_prediction(Image.fromarray(img), 384, 512)
     assert invert is True and pred.shape == (384, 320) and pred.dtype == np.float32
     want, _ = ozd.get_raw_prediction(img, sd, 384, 512, core_name='beitl16_384')
-    precision.check("zoedepth_nk beitl16_384 (384x320 image)", pred, want)
+    ref16 = precision.reference_fp16_error_zoe(img, sd, 384, 512, 'beitl16_384', want, cuda_device)
+    precision.check("zoedepth_nk beitl16_384 (384x320 image)", pred, want, ref16)
     mh.unload_models()
