@@ -293,6 +293,165 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+class Gatherer:
+    """The path's one exchange (north_star): ONE NCCL all-gather per batch of the finished tensors, packed into a single
+    buffer, issued on a SIDE stream so that it overlaps the next batch's compute.  The compute stream
+    only waits for the cheap device-to-device pack of the previous batch before it overwrites the outputs."""
+
+    def __init__(self, world, dev):
+        import torch
+        self.world, self.dev = world, dev
+        self.side = torch.cuda.Stream(device=dev)
+        self.pack = [None, None]
+        self.gathered = [None, None]
+        self.pack_done = [None, None]
+        self.k = 0
+        self.bytes_per_rank = 0
+
+    def submit(self, outs):
+        import torch
+        import torch.distributed as dist
+        flat = [o.reshape(-1).view(torch.uint8) if o.dtype != torch.uint8 else o.reshape(-1) for o in outs]
+        total = sum(f.numel() for f in flat)
+        k = self.k & 1
+        if self.pack[k] is None or self.pack[k].numel() != total:
+            self.pack[k] = torch.empty(total, dtype=torch.uint8, device=self.dev)
+            self.gathered[k] = torch.empty(self.world * total, dtype=torch.uint8, device=self.dev)
+        self.bytes_per_rank = total
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            off = 0
+            for f in flat:
+                self.pack[k][off:off + f.numel()].copy_(f, non_blocking=True)
+                off += f.numel()
+            done = torch.cuda.Event()
+            done.record(self.side)
+            dist.all_gather_into_tensor(self.gathered[k], self.pack[k])
+        main.wait_event(done)            # the next batch may overwrite `outs` once they are packed; the gather itself overlaps it
+        self.pack_done[k] = done
+        self.k += 1
+        return self.gathered[k]
+
+    def drain(self):
+        import torch
+        torch.cuda.current_stream().wait_stream(self.side)
+
+
+def measure(wl, args, world, dev, rank, local_rank, peaks, steps, with_cpu_baseline, with_funnel):
+    """One workload: resident-input throughput, dominant-kernel roofline, host-buffer e2e (+ funnel e2e, CPU baseline)."""
+    import torch
+    import torch.distributed as dist
+    graphed = None
+    if not args.no_graph:
+        graphed = GraphedStep(lambda: wl.step_resident(False))
+    gatherer = Gatherer(world, dev) if world > 1 else None
+
+    def full_step(time_kernel=False):
+        outs = wl.step_resident(True) if (time_kernel or graphed is None) else graphed()
+        if gatherer is not None:
+            gatherer.submit(outs)
+        return outs
+
+    for _ in range(args.warmup):
+        full_step()
+    if gatherer is not None:
+        gatherer.drain()
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs ------------------------------------------------------------------
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        full_step(time_kernel=False)
+    if gatherer is not None:
+        gatherer.drain()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / steps
+
+    # ---- dominant-kernel probe: same kernels, eager, CUDA events around the launches (events cannot be captured) ----
+    roofline = None
+    if rank == 0:
+        if hasattr(wl, "probe"):
+            roofline = wl.roofline_from_probe(peaks, wl.probe(3), ms_step)
+        else:
+            evs = []
+            for _ in range(3):
+                wl.step_resident(True)
+                evs.append(wl._ev)
+            torch.cuda.synchronize()
+            roofline = wl.roofline(peaks, float(np.mean([a.elapsed_time(b) for a, b in evs])))
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region ----------------------------------------------------
+    for _ in range(2):
+        wl.step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        wl.step_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item()) / steps
+    h2d, d2h = wl.e2e_bytes()
+    if rank != 0:
+        return None
+    value = wl.B * world / (ms_step * 1e-3)
+    line = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
+            "clocks": clocks, "gpu_launches": (wl.launches_per_step or 0) * steps,
+            "launch_mode": "cuda_graph" if (graphed is not None and graphed.graph is not None) else "eager",
+            "e2e": {"value": wl.B * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                    "api": "public batched API (ModelHolder / create_*_batch) from pinned host buffers, H2D + D2H in the timed region"}}
+    if roofline is not None:
+        line["roofline"] = roofline
+    if gatherer is not None:
+        line["collective"] = {"backend": "nccl", "nccl_version": ".".join(str(v) for v in torch.cuda.nccl.version()),
+                              "op": "all_gather_into_tensor, one per batch, packed buffer, side stream overlapped with the next batch",
+                              "bytes_per_rank_per_step": gatherer.bytes_per_rank}
+    if hasattr(wl, "extra"):
+        line.update(wl.extra(ms_step, peaks))
+    if with_funnel and world == 1 and hasattr(wl, "funnel_e2e"):
+        try:
+            line["e2e_funnel"] = wl.funnel_e2e(2)
+        except Exception as e:  # noqa: BLE001
+            line["e2e_funnel"] = {"error": str(e)[:200]}
+    if world == 1 and with_cpu_baseline:
+        import oracle
+        oracle.build()
+        cores = pick_torch_threads(host_threads())
+        wl.cpu_sample(cores)
+        n, dt = wl.cpu_sample(cores)
+        line["cpu_baseline"] = {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{n} image(s) of the same workload through oracle/ (restatement of the reference CPU path: fp32 torch network, C + OpenMP stereo / normal map / normalise), {dt:.2f} s"}
+    return line
+
+
+# sub-benchmarks carried in the default run so that the driver's record covers BASELINE's "depth+stereo 512^2 & 2048^2"
+SUB_WORKLOADS = {"depth_beit512": ["stereo2048", "dav2_stereo"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,6 +460,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-benchmarks (stereo2048, dav2_stereo) of the default run")
+    ap.add_argument("--no-funnel", action="store_true", help="skip the core_generation_funnel (PIL in / PIL out) end-to-end measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -329,94 +490,24 @@ def main():
         dist.barrier()
     peaks = _peaks()
     wl = WORKLOADS[args.workload](dev, rank)
-
-    gather_bufs = None
-    graphed = None
-    if not args.no_graph:
-        graphed = GraphedStep(lambda: wl.step_resident(False))
-
-    def full_step(time_kernel=False):
-        outs = wl.step_resident(True) if (time_kernel or graphed is None) else graphed()
-        if world > 1:  # the path's one exchange: all-gather of the finished tensors over NVLink
-            nonlocal gather_bufs
-            flat = [o.reshape(-1).view(torch.uint8) if o.dtype != torch.uint8 else o.reshape(-1) for o in outs]
-            if gather_bufs is None:
-                gather_bufs = [torch.empty(world * f.numel(), dtype=torch.uint8, device=dev) for f in flat]
-            for f, g in zip(flat, gather_bufs):
-                dist.all_gather_into_tensor(g, f)
-        return outs
-
-    for _ in range(args.warmup):
-        full_step()
-    torch.cuda.synchronize()
-
-    # ---- timed region: device-resident inputs ------------------------------------------------------------------
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_events = []
-    e0.record()
-    for _ in range(args.steps):
-        full_step(time_kernel=False)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if sampler else None
-    # dominant-kernel probe: same launches, eager, CUDA events around the one kernel (events cannot be captured)
-    for _ in range(3):
-        full_step(time_kernel=True)
-        if hasattr(wl, "_ev"):
-            kernel_events.append(wl._ev)
-    torch.cuda.synchronize()
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events])) if kernel_events else None
-
-    # ---- e2e: host buffers, H2D + D2H inside the timed region ----------------------------------------------------
-    for _ in range(2):
-        wl.step_e2e()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        wl.step_e2e()
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item()) / args.steps
-    h2d, d2h = wl.e2e_bytes()
-
+    line = measure(wl, args, world, dev, rank, local_rank, peaks, args.steps, not args.no_cpu_baseline, not args.no_funnel)
+    if rank == 0 and world == 1 and not args.no_sub:
+        subs = []
+        for name in SUB_WORKLOADS.get(args.workload, []):
+            del wl
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            try:
+                wl = WORKLOADS[name](dev, rank)
+                sub = measure(wl, args, world, dev, rank, local_rank, peaks, max(2, min(args.steps, 5)), not args.no_cpu_baseline, False)
+                sub["workload"] = name
+                subs.append(sub)
+            except Exception as e:  # noqa: BLE001
+                subs.append({"workload": name, "error": str(e)[:300]})
+                wl = None
+        line["sub_benchmarks"] = subs
     if rank == 0:
-        value = wl.B * world / (ms_step * 1e-3)
-        line = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
-                "clocks": clocks, "gpu_launches": wl.launches_per_step * args.steps,
-                "launch_mode": "cuda_graph" if (graphed is not None and graphed.graph is not None) else "eager",
-                "e2e": {"value": wl.B * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e}}
-        if kernel_ms is not None:
-            line["roofline"] = wl.roofline(peaks, kernel_ms)
-        if hasattr(wl, "extra"):
-            line.update(wl.extra(ms_step, peaks))
-        if world == 1 and not args.no_cpu_baseline:
-            import oracle
-            oracle.build()
-            cores = pick_torch_threads(host_threads())
-            wl.cpu_sample(cores)
-            n, dt = wl.cpu_sample(cores)
-            line["cpu_baseline"] = {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n} image(s) of the same workload through oracle/ (C restatement of the reference CPU path, OpenMP over rows), {dt:.2f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

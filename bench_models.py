@@ -1,4 +1,9 @@
-"""Depth-network workloads for bench.py (kept separate so bench.py stays importable before the tensor-core path exists)."""
+"""Depth-network workloads for bench.py (kept separate so bench.py stays importable before the tensor-core path exists).
+
+Timed region: the model-level C-ABI handle (NativeDepthModel -> dm_depth_forward) + the HBM-side kernels.  A second, op-level
+instance of the same network (the Python engine that issues the same kernels one C call at a time) exists only for the PROBE
+pass after the timed region: CUDA events around every attention launch and around the block-0 fc1 GEMM, which gives the
+dominant kernel's share of the step and its roofline live, in this run."""
 from __future__ import annotations
 
 import os
@@ -10,7 +15,80 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 
 
-class Dav2Stereo:
+class _NetWorkload:
+    """Shared parts of the network workloads: native model for the timed region, op-level engine for the kernel probe."""
+    heads = 16
+    C = 1024
+
+    def _probe_step(self, run_engine):
+        """one eager op-level forward with events around the attention launches and the block-0 fc1"""
+        import torch
+        self.engine.probe = {'attn': [], 'fc1': (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_engine()
+        e1.record()
+        pr, self.engine.probe = self.engine.probe, None
+        return pr, (e0, e1)
+
+    def probe(self, n=3):
+        """-> dict(attn_ms_per_launch, attn_launches, fc1_ms, forward_ms): mean over n eager op-level forwards"""
+        import torch
+        acc = []
+        for _ in range(n):
+            acc.append(self._probe_step(self._engine_forward))
+        torch.cuda.synchronize()
+        attn = [np.mean([a.elapsed_time(b) for a, b in pr['attn']]) for pr, _ in acc]
+        fc1 = [pr['fc1'][0].elapsed_time(pr['fc1'][1]) for pr, _ in acc]
+        fwd = [a.elapsed_time(b) for _, (a, b) in acc]
+        return {"attn_ms_per_launch": float(np.mean(attn)), "attn_launches": len(acc[0][0]['attn']), "fc1_ms": float(np.mean(fc1)),
+                "forward_ms": float(np.mean(fwd))}
+
+    def roofline_from_probe(self, peaks, pr, ms_step):
+        """Dominant kernel = the fused attention kernel (largest share of the step, measured here); fc1 reported beside it."""
+        N = self.N
+        attn_flops = 4.0 * self.B * self.heads * N * N * 64          # QK^T + PV, 2 flops per MAC (SURVEY 8d: 2.15 + 2.15 GFLOP / image / block)
+        a = attn_flops / (pr["attn_ms_per_launch"] * 1e-3) / 1e12
+        f = self.fc1_flops / (pr["fc1_ms"] * 1e-3) / 1e12
+        share = pr["attn_ms_per_launch"] * pr["attn_launches"] / pr["forward_ms"]
+        return {"bound": "tensor", "kernel": self.ATTN_KERNEL, "achieved": a, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": a / peaks["bf16_tflops"], "traffic": None, "traffic_note": "see profiles/r02_ncu_attention_fwd4.txt (one ncu --set full capture per kernel)",
+                "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "algorithmic_flops_per_launch": attn_flops,
+                "kernel_ms": pr["attn_ms_per_launch"], "launches_per_step": pr["attn_launches"],
+                "share_of_step": share, "share_note": "sum of the attention launches / eager op-level forward, CUDA events, this run",
+                "secondary": {"kernel": self.FC1_KERNEL, "achieved": f, "frac": f / peaks["bf16_tflops"], "kernel_ms": pr["fc1_ms"],
+                              "algorithmic_flops_per_launch": self.fc1_flops}}
+
+    def extra(self, ms_step, peaks):
+        fwd = self.FLOP_PER_IMAGE * self.B / (ms_step * 1e-3) / 1e12
+        return {"whole_step_tflops": fwd, "whole_step_frac_of_sustained_peak": fwd / peaks["bf16_tflops_sustained"]}
+
+    def funnel_e2e(self, steps=2):
+        """The reference-facing entry point itself: PIL images in, PIL images out through core_generation_funnel (src/core.py:83)."""
+        import torch
+        from PIL import Image
+        from depthmap_b200 import core
+        holder = core.get_model_holder()
+        holder.unload_models()
+        holder.weights_provider = lambda t: self._state_dict()
+        imgs = [Image.fromarray(self.rgb_h[i].numpy()) for i in range(self.B)]
+        inp = self.funnel_options()
+        n_out = 0
+        times = []
+        for it in range(steps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_out = sum(1 for _ in core.core_generation_funnel(None, list(imgs), None, None, inp, ops={}))
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        holder.unload_models()
+        holder.weights_provider = None
+        dt = float(np.mean(times[1:]))             # first pass loads / packs the model, as the reference's first call does
+        return {"value": self.B / dt, "unit": "images/s", "ms_per_step": dt * 1e3, "results_per_step": n_out,
+                "note": "core_generation_funnel(PIL in -> PIL out), wall clock incl. PIL<->tensor conversion, H2D/D2H and the funnel's bounded batches"}
+
+
+class Dav2Stereo(_NetWorkload):
     """BASELINE.json configs[2]: depth_anything_v2 vitl @518x518 + SBS stereo (divergence 2.5, polylines fill) + normal map,
     batch 64 per GPU."""
     name = "dav2_stereo"
@@ -20,15 +98,26 @@ class Dav2Stereo:
     dtype = "fp16"  # tensor-core operands fp16, fp32 accumulate / residual stream (the reference's GPU path is .half())
     fill = "polylines_sharp"
     FLOP_PER_IMAGE = 1304.2e9  # SURVEY §8d, cross-checked there against FlopCounterMode on the reference module
+    MODEL_TYPE = 14
+    ATTN_KERNEL = "attention_fwd4_kernel<0> (fused softmax(QK^T)V, tcgen05 + TMEM, N = 1370, 16 heads x 64)"
+    FC1_KERNEL = "gemm_tcgen05_2sm_kernel (cta_group::2, 256x256 tile pair; block-0 MLP fc1: M=B*1370, N=4096, K=1024, GELU epilogue)"
+
+    def _state_dict(self):
+        from oracle import synth_weights  # synthetic checkpoint-layout weights (data generation, not compute)
+        return synth_weights.make_dav2_state_dict(self.encoder, seed=0)
+
+    def funnel_options(self):
+        return dict(compute_device='GPU', model_type=self.MODEL_TYPE, net_width=self.W, net_height=self.H, do_output_depth=True,
+                    gen_stereo=True, stereo_modes=['left-right'], stereo_divergence=2.5, stereo_fill_algo=self.fill, gen_normalmap=True)
 
     def __init__(self, dev, rank):
         import torch
         from bench import make_images
-        from depthmap_b200.depthmap_generation import DepthAnythingV2Engine
-        from oracle import synth_weights  # synthetic checkpoint-layout weights (data generation, not compute)
+        from depthmap_b200.depthmap_generation import DepthAnythingV2Engine, NativeDepthModel
         self.dev = dev
-        sd = synth_weights.make_dav2_state_dict(self.encoder, seed=0)
-        self.engine = DepthAnythingV2Engine(sd, self.encoder, dev)
+        sd = self._state_dict()
+        self.model = NativeDepthModel(sd, self.MODEL_TYPE, dev)
+        self.engine = DepthAnythingV2Engine(sd, self.encoder, dev)      # probe pass only
         del sd
         rgb, _ = make_images(self.B, self.H, self.W, rank)
         self.rgb_h = torch.from_numpy(rgb).pin_memory()
@@ -50,17 +139,18 @@ class Dav2Stereo:
         from depthmap_b200.core import normalize_prediction_batch
         from depthmap_b200.normalmap_generation import create_normalmap_batch
         from depthmap_b200.stereoimage_generation import create_stereoimages_batch
-        n0 = self.engine.ops.launches
-        if time_kernel:
-            self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            self.engine.probe = {'fc1': self._ev}
-        pred = self.engine.forward_batch(rgb, self.W)
-        self.engine.probe = None
+        n0 = self.model.launches
+        pred = self.model.forward_batch(rgb, self.W, self.H)
         depth = normalize_prediction_batch(pred, False)
         sbs = create_stereoimages_batch(rgb, depth, 2.5, 0.0, ['left-right'], 0.0, 1.0, self.fill)[0]
         normal = create_normalmap_batch(depth)
-        self.launches_per_step = (self.engine.ops.launches - n0) + 3 + 3 + 1
+        n1 = self.model.launches
+        if n1 > n0:
+            self.launches_per_step = (n1 - n0) + 3 + 3 + 1
         return depth, sbs, normal
+
+    def _engine_forward(self):
+        return self.engine.forward_batch(self.rgb, self.W)
 
     def step_resident(self, time_kernel=False):
         return self.step(self.rgb, time_kernel)
@@ -72,17 +162,6 @@ class Dav2Stereo:
 
     def e2e_bytes(self):
         return self.rgb_h.numel(), self.B * self.H * self.W * (2 + 6 + 3)
-
-    def roofline(self, peaks, kernel_ms):
-        achieved = self.fc1_flops / (kernel_ms * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": "gemm_tcgen05_2sm_kernel (cta_group::2, 256x256 tile pair; block-0 MLP fc1: M=B*1370, N=4096, K=1024, GELU epilogue)",
-                "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": None, "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "algorithmic_flops_per_launch": self.fc1_flops,
-                "kernel_ms": kernel_ms}
-
-    def extra(self, ms_step, peaks):
-        fwd = self.FLOP_PER_IMAGE * self.B / (ms_step * 1e-3) / 1e12
-        return {"whole_step_tflops": fwd, "whole_step_frac_of_sustained_peak": fwd / peaks["bf16_tflops_sustained"]}
 
     def cpu_sample(self, nthreads):
         """reference CPU path on one image: fp32 torch forward (oracle restatement) + C oracle stereo / normal map."""
@@ -103,23 +182,33 @@ class Dav2Stereo:
         return 1, time.perf_counter() - t0
 
 
-class DepthBeit512:
+class DepthBeit512(_NetWorkload):
     """BASELINE.json configs[1]: dpt_beit_large_512 @512x512, batch 32 per GPU, depth only (prediction -> 16-bit depth)."""
     name = "depth_beit512"
-    model = "beitl16_512"
+    model_name = "beitl16_512"
     H = W = 512
     B = 32
     dtype = "fp16"
     FLOP_PER_IMAGE = 962.7e9  # SURVEY §8d
+    MODEL_TYPE = 1
+    ATTN_KERNEL = "attention_fwd4_kernel<3> (fused softmax(QK^T + rel-pos bias)V, tcgen05 + TMEM, N = 1025, 16 heads x 64; + class-row kernel)"
+    FC1_KERNEL = "gemm_tcgen05_2sm_kernel (cta_group::2, 256x256 tile pair; block-0 MLP fc1: M=B*1025, N=4096, K=1024, GELU epilogue)"
+
+    def _state_dict(self):
+        from oracle import synth_weights  # synthetic checkpoint-layout weights (data generation, not compute)
+        return synth_weights.make_beit_dpt_state_dict(self.model_name, seed=0)
+
+    def funnel_options(self):
+        return dict(compute_device='GPU', model_type=self.MODEL_TYPE, net_width=self.W, net_height=self.H, do_output_depth=True)
 
     def __init__(self, dev, rank):
         import torch
         from bench import make_images
-        from depthmap_b200.depthmap_generation import DptBeitEngine
-        from oracle import synth_weights  # synthetic checkpoint-layout weights (data generation, not compute)
+        from depthmap_b200.depthmap_generation import DptBeitEngine, NativeDepthModel
         self.dev = dev
-        sd = synth_weights.make_beit_dpt_state_dict(self.model, seed=0)
-        self.engine = DptBeitEngine(sd, self.model, dev)
+        sd = self._state_dict()
+        self.model = NativeDepthModel(sd, self.MODEL_TYPE, dev)
+        self.engine = DptBeitEngine(sd, self.model_name, dev)           # probe pass only
         del sd
         rgb, _ = make_images(self.B, self.H, self.W, rank)
         self.rgb_h = torch.from_numpy(rgb).pin_memory()
@@ -137,15 +226,16 @@ class DepthBeit512:
     def step(self, rgb, time_kernel=False):
         import torch
         from depthmap_b200.core import normalize_prediction_batch
-        n0 = self.engine.ops.launches
-        if time_kernel:
-            self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            self.engine.probe = {'fc1': self._ev}
-        pred = self.engine.forward_batch(rgb, self.W, self.H)
-        self.engine.probe = None
+        n0 = self.model.launches
+        pred = self.model.forward_batch(rgb, self.W, self.H)
         depth = normalize_prediction_batch(pred, False)
-        self.launches_per_step = (self.engine.ops.launches - n0) + 3
+        n1 = self.model.launches
+        if n1 > n0:
+            self.launches_per_step = (n1 - n0) + 3
         return (depth,)
+
+    def _engine_forward(self):
+        return self.engine.forward_batch(self.rgb, self.W, self.H)
 
     def step_resident(self, time_kernel=False):
         return self.step(self.rgb, time_kernel)
@@ -158,20 +248,6 @@ class DepthBeit512:
     def e2e_bytes(self):
         return self.rgb_h.numel(), self.B * self.H * self.W * 2
 
-    def roofline(self, peaks, kernel_ms):
-        achieved = self.fc1_flops / (kernel_ms * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": "gemm_tcgen05_2sm_kernel (cta_group::2, 256x256 tile pair; block-0 MLP fc1: M=B*1025, N=4096, K=1024, GELU epilogue)",
-                "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch (B = 32), profiles/r01_ncu_gemm_2sm_fc1.txt;
-                # algorithmic: A 67 MB + W 8 MB in, C 269 MB out
-                "traffic": 316.4e6 if self.B == 32 else None, "traffic_unit": "bytes/launch (ncu --set full)",
-                "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "algorithmic_flops_per_launch": self.fc1_flops,
-                "kernel_ms": kernel_ms}
-
-    def extra(self, ms_step, peaks):
-        fwd = self.FLOP_PER_IMAGE * self.B / (ms_step * 1e-3) / 1e12
-        return {"whole_step_tflops": fwd, "whole_step_frac_of_sustained_peak": fwd / peaks["bf16_tflops_sustained"]}
-
     def cpu_sample(self, nthreads):
         """reference CPU path on one image: fp32 torch forward (oracle restatement of DPT-BEiT) + C oracle normalise."""
         import torch
@@ -179,11 +255,11 @@ class DepthBeit512:
         from oracle import normalmap as onm
         from oracle import synth_weights
         if not hasattr(self, "_sd_cpu"):
-            self._sd_cpu = synth_weights.make_beit_dpt_state_dict(self.model, seed=0)
+            self._sd_cpu = synth_weights.make_beit_dpt_state_dict(self.model_name, seed=0)
         rgb = self.rgb_h[0].numpy()
         torch.set_num_threads(nthreads)
         t0 = time.perf_counter()
-        pred, inv = beit_dpt.get_raw_prediction(rgb, self._sd_cpu, self.model, self.W, self.H)
+        pred, inv = beit_dpt.get_raw_prediction(rgb, self._sd_cpu, self.model_name, self.W, self.H)
         onm.normalize_to_u16(pred, inv)
         return 1, time.perf_counter() - t0
 
@@ -194,6 +270,8 @@ class Dav2StereoSmall(Dav2Stereo):
     encoder = "vits"
     B = 8
     FLOP_PER_IMAGE = 0.0
+    MODEL_TYPE = 12
+    heads, C = 6, 384
 
 
 MODEL_WORKLOADS = {"depth_beit512": DepthBeit512, "dav2_stereo": Dav2Stereo, "dav2s_stereo": Dav2StereoSmall}

@@ -246,6 +246,11 @@ typedef struct dm_weight_blob {
     int32_t count;
 } dm_weight_blob;
 typedef struct dm_model dm_model_t;
+/* Resolution-dependent tables exactly as the model computes them (HOST pointers, float32 arithmetic in torch's order):
+ * DINOv2 interpolate_pos_encoding (dinov2.py:179-210): pos_embed [1 + n*n, C] -> out [1 + gh*gw, C];
+ * BEiT _get_rel_pos_bias table half (dmidas/backbones/beit.py:29-50): table [(2w-1)^2 + 3, heads] -> out [heads, (2gh-1)(2gw-1)+3] * log2(e). */
+int dm_dinov2_pos_embed(const float *pos_embed_host, int n, int C, int gh, int gw, float *out_host);
+int dm_beit_rel_table(const float *table_host, int window, int heads, int gh, int gw, float *out_host);
 int dm_model_create(dm_model_t **out, int model_type, const dm_weight_blob *weights, int device, int dtype);
 int dm_model_destroy(dm_model_t *model);
 int dm_model_net_size(const dm_model_t *model, int W, int H, int net_w, int net_h, int *nw_out, int *nh_out);

@@ -105,6 +105,7 @@ struct dm_model {
     std::vector<void *> tab_owned;             // tables of the current resolution
     float *pos_dev = nullptr; int pos_gh = -1, pos_gw = -1;
     std::map<dm::GraphKey, dm::GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;         // graphs are captured on the model's own stream (the caller's may be the legacy default stream, which cannot capture)
     long long launches = 0;
 };
 
@@ -310,25 +311,30 @@ static void bilinear_table(const float *src, int ih, int iw, float *dst, int oh,
     }
 }
 
-// BEiT: per block the [nrd, heads] table resized to the current window (dmidas/backbones/beit.py:29-50), laid out
-// [heads, nrd] and multiplied by log2(e).  Once per resolution.
+// BEiT: the [nrd0, heads] table of one block resized to the current window (dmidas/backbones/beit.py:29-50), laid out
+// [heads, nrd] and multiplied by log2(e).  Host arithmetic, float32, in torch's operation order.
+static void beit_rel_table_host(const float *t, int window, int heads, int gh, int gw, float *out) {
+    const int old = 2 * window - 1, nh = 2 * gh - 1, nw = 2 * gw - 1, nrd = nh * nw + 3;
+    std::vector<float> plane((size_t)old * old), res((size_t)nh * nw);
+    for (int hd = 0; hd < heads; ++hd) {
+        // sub = table[:old*old].reshape(1, old_w, old_h, heads).permute(0, 3, 1, 2): plane[a][b] = table[a*old + b][hd]
+        for (int a = 0; a < old * old; ++a) plane[a] = t[(size_t)a * heads + hd];
+        if (nh == old && nw == old) res = plane; else bilinear_table(plane.data(), old, old, res.data(), nh, nw);
+        for (int a = 0; a < nh * nw; ++a) out[(size_t)hd * nrd + a] = res[a] * 1.4426950408889634f;
+        for (int e = 0; e < 3; ++e) out[(size_t)hd * nrd + nh * nw + e] = t[(size_t)(old * old + e) * heads + hd] * 1.4426950408889634f;
+    }
+}
+
 static int ensure_rel_tables(dm_model *m, int gh, int gw) {
     if (m->tab_gh == gh && m->tab_gw == gw) return DM_OK;
     const ModelCfg &c = m->cfg;
-    const int old = 2 * c.window - 1, nh = 2 * gh - 1, nw = 2 * gw - 1, nrd = nh * nw + 3, heads = c.heads;
+    const int nrd = (2 * gh - 1) * (2 * gw - 1) + 3, heads = c.heads;
     m->rel_tab.assign(c.depth, nullptr);
     for (void *p : m->tab_owned) cudaFree(p);      // the tables of the previous resolution (no graph of that resolution survives: ensure_buffers ran first)
     m->tab_owned.clear();
-    std::vector<float> plane((size_t)old * old), res((size_t)nh * nw), out((size_t)heads * nrd);
+    std::vector<float> out((size_t)heads * nrd);
     for (int i = 0; i < c.depth; ++i) {
-        const std::vector<float> &t = m->blocks[i].rel_table_host;
-        for (int hd = 0; hd < heads; ++hd) {
-            // sub = table[:old*old].reshape(1, old_w, old_h, heads).permute(0, 3, 1, 2): plane[a][b] = table[a*old + b][hd]
-            for (int a = 0; a < old * old; ++a) plane[a] = t[(size_t)a * heads + hd];
-            if (nh == old && nw == old) res = plane; else bilinear_table(plane.data(), old, old, res.data(), nh, nw);
-            for (int a = 0; a < nh * nw; ++a) out[(size_t)hd * nrd + a] = res[a] * 1.4426950408889634f;
-            for (int e = 0; e < 3; ++e) out[(size_t)hd * nrd + nh * nw + e] = t[(size_t)(old * old + e) * heads + hd] * 1.4426950408889634f;
-        }
+        beit_rel_table_host(m->blocks[i].rel_table_host.data(), c.window, heads, gh, gw, out.data());
         DM_TRY(upload(m->tab_owned, out.data(), out.size() * 4, (void **)&m->rel_tab[i]));
     }
     m->tab_gh = gh; m->tab_gw = gw; m->nrd = nrd;
@@ -344,40 +350,43 @@ static void cubic_w(float x, float *c) {
     c[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
     c[3] = ((A * (2.f - x) - 5.f * A) * (2.f - x) + 8.f * A) * (2.f - x) - 4.f * A;
 }
-static int ensure_pos(dm_model *m, int gh, int gw) {
-    if (m->pos_gh == gh && m->pos_gw == gw) return DM_OK;
-    const int C = m->cfg.C, n = m->pos_n;
-    std::vector<float> out((size_t)(gh * gw + 1) * C);
-    const float *pe = m->pos_embed_host.data();
+static void dinov2_pos_embed_host(const float *pe, int n, int C, int gh, int gw, float *out) {
     for (int k = 0; k < C; ++k) out[k] = pe[k];
     if (gh == n && gw == n) {
-        memcpy(out.data() + C, pe + C, (size_t)n * n * C * sizeof(float));
-    } else {
-        // the reference hands (w, h) = (tensor H, tensor W) to the function, so the FIRST spatial axis of the n x n grid follows gh
-        const double sf_y = ((double)gh + 0.1) / sqrt((double)(n * n)), sf_x = ((double)gw + 0.1) / sqrt((double)(n * n));
-        const float sy = (float)(1.0 / sf_y), sx = (float)(1.0 / sf_x);
-        for (int y = 0; y < gh; ++y) {
-            const float fy = sy * ((float)y + 0.5f) - 0.5f;
-            const int iy = (int)floorf(fy);
-            float cy[4]; cubic_w(fy - (float)iy, cy);
-            for (int x = 0; x < gw; ++x) {
-                const float fx = sx * ((float)x + 0.5f) - 0.5f;
-                const int ix = (int)floorf(fx);
-                float cx[4]; cubic_w(fx - (float)ix, cx);
-                float *o = out.data() + (size_t)(1 + y * gw + x) * C;
-                for (int k = 0; k < C; ++k) o[k] = 0.f;
-                for (int j = 0; j < 4; ++j) {
-                    const int yy = std::min(std::max(iy - 1 + j, 0), n - 1);
-                    for (int i = 0; i < 4; ++i) {
-                        const int xx = std::min(std::max(ix - 1 + i, 0), n - 1);
-                        const float wgt = cy[j] * cx[i];
-                        const float *s = pe + (size_t)(1 + yy * n + xx) * C;
-                        for (int k = 0; k < C; ++k) o[k] += wgt * s[k];
-                    }
+        memcpy(out + C, pe + C, (size_t)n * n * C * sizeof(float));
+        return;
+    }
+    // the reference hands (w, h) = (tensor H, tensor W) to the function, so the FIRST spatial axis of the n x n grid follows gh
+    const double sf_y = ((double)gh + 0.1) / sqrt((double)(n * n)), sf_x = ((double)gw + 0.1) / sqrt((double)(n * n));
+    const float sy = (float)(1.0 / sf_y), sx = (float)(1.0 / sf_x);
+    for (int y = 0; y < gh; ++y) {
+        const float fy = sy * ((float)y + 0.5f) - 0.5f;
+        const int iy = (int)floorf(fy);
+        float cy[4]; cubic_w(fy - (float)iy, cy);
+        for (int x = 0; x < gw; ++x) {
+            const float fx = sx * ((float)x + 0.5f) - 0.5f;
+            const int ix = (int)floorf(fx);
+            float cx[4]; cubic_w(fx - (float)ix, cx);
+            float *o = out + (size_t)(1 + y * gw + x) * C;
+            for (int k = 0; k < C; ++k) o[k] = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const int yy = std::min(std::max(iy - 1 + j, 0), n - 1);
+                for (int i = 0; i < 4; ++i) {
+                    const int xx = std::min(std::max(ix - 1 + i, 0), n - 1);
+                    const float wgt = cy[j] * cx[i];
+                    const float *s = pe + (size_t)(1 + yy * n + xx) * C;
+                    for (int k = 0; k < C; ++k) o[k] += wgt * s[k];
                 }
             }
         }
     }
+}
+
+static int ensure_pos(dm_model *m, int gh, int gw) {
+    if (m->pos_gh == gh && m->pos_gw == gw) return DM_OK;
+    const int C = m->cfg.C;
+    std::vector<float> out((size_t)(gh * gw + 1) * C);
+    dinov2_pos_embed_host(m->pos_embed_host.data(), m->pos_n, C, gh, gw, out.data());
     for (void *p : m->tab_owned) cudaFree(p);
     m->tab_owned.clear();
     DM_TRY(upload(m->tab_owned, out.data(), out.size() * 4, (void **)&m->pos_dev));
@@ -561,10 +570,23 @@ DM_EXPORT int dm_model_create(dm_model_t **out, int model_type, const dm_weight_
 DM_EXPORT int dm_model_destroy(dm_model_t *m) {
     if (!m) return DM_OK;
     for (auto &g : m->graphs) { if (g.second.exec) cudaGraphExecDestroy(g.second.exec); }
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     for (void *p : m->buf_owned) cudaFree(p);
     for (void *p : m->tab_owned) cudaFree(p);
     for (void *p : m->owned) cudaFree(p);
     delete m;
+    return DM_OK;
+}
+
+/* resolution-dependent tables as the model builds them (host arithmetic); exported so the op-level path uses the very same numbers */
+DM_EXPORT int dm_dinov2_pos_embed(const float *pos_embed_host, int n, int C, int gh, int gw, float *out_host) {
+    if (!pos_embed_host || !out_host || n <= 0 || C <= 0 || gh <= 0 || gw <= 0) { dm::set_error("dm_dinov2_pos_embed: bad arguments"); return DM_E_INVALID; }
+    dm::dinov2_pos_embed_host(pos_embed_host, n, C, gh, gw, out_host);
+    return DM_OK;
+}
+DM_EXPORT int dm_beit_rel_table(const float *table_host, int window, int heads, int gh, int gw, float *out_host) {
+    if (!table_host || !out_host || window <= 0 || heads <= 0 || gh <= 0 || gw <= 0) { dm::set_error("dm_beit_rel_table: bad arguments"); return DM_E_INVALID; }
+    dm::beit_rel_table_host(table_host, window, heads, gh, gw, out_host);
     return DM_OK;
 }
 
@@ -609,9 +631,10 @@ DM_EXPORT int dm_depth_forward(dm_model_t *m, const uint8_t *rgb, int B, int H, 
         DM_TRY(dev_alloc(m->buf_owned, in_bytes, &g.in));
         DM_TRY(dev_alloc(m->buf_owned, out_bytes, (void **)&g.out));
         cudaGraph_t graph = nullptr;
-        DM_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        const int rc = run_forward(m, (const uint8_t *)g.in, B, H, W, nw, nh, g.out, out_h, out_w, st);
-        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (!m->cap_stream) DM_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+        DM_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_forward(m, (const uint8_t *)g.in, B, H, W, nw, nh, g.out, out_h, out_w, m->cap_stream);
+        cudaError_t e = cudaStreamEndCapture(m->cap_stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture (dm_depth_forward)");
         e = cudaGraphInstantiate(&g.exec, graph, 0);

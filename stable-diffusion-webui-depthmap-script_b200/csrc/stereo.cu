@@ -133,7 +133,7 @@ __device__ __forceinline__ uint8_t f64_to_u8_wrap(double v) {
 extern __shared__ __align__(16) uint8_t g_smem[];
 
 struct RowSmem {
-    uint32_t src;      // u8  [3W]
+    uint32_t src;      // u8  [3W] (naive family)  |  u32 [W] R | G<<8 | B<<16 (polylines)
     uint32_t eye[2];   // u8  [3W] each
     uint32_t ndp;      // f64 [W]   nd ** exponent
     uint32_t xs;       // f64 [n]   vertex x in original order (polylines)
@@ -155,26 +155,21 @@ struct NdSrc {
     const double *ndp;
     const uint16_t *dep;
     uint32_t mn;
-    double den, expo;
+    double den, rden, expo;     // rden = 1 / den, correctly rounded
     int pow_kind;
     __device__ __forceinline__ double get(int col) const {
         if (ndp) return ndp[col];
-        const double nd = (double)((uint32_t)dep[col] - mn) / den;
-        return pow_ref(nd, expo, pow_kind);
+        // (d - min) / (max - min) as the reference's float64 true-divide (:81), without the division: with r = RN(1/den),
+        // q0 = RN(a r), the residual a - q0 den is exact in one FMA and RN(q0 + residual r) is the correctly rounded quotient
+        // (Markstein); checked for EVERY pair 0 <= a <= den <= 65535 on the CPU (tests/test_exact_division.py).
+        const double a = (double)((uint32_t)dep[col] - mn);
+        const double q0 = __dmul_rn(a, rden);
+        const double rem = __fma_rn(-q0, den, a);
+        return pow_ref(__fma_rn(rem, rden, q0), expo, pow_kind);
     }
 };
 
-// :177-192 vertex x in ORIGINAL order (t = 0 and t = n-1 are the sentinels)
-template <bool SHARP>
-__device__ __forceinline__ double vertex_x(int t, int n, int W, const NdSrc &nds, double div_px, double sep_px) {
-    if (t == 0) return -1.0 * (double)W;
-    if (t == n - 1) return 2.0 * (double)W;
-    const int col = SHARP ? ((t - 1) >> 1) : (t - 1);
-    const double coord_d = nds.get(col) * div_px;
-    const double coord_x = (double)col + 0.5 + coord_d + sep_px;
-    if (!SHARP) return coord_x;
-    return ((t - 1) & 1) ? coord_x + 0.45 : coord_x - 0.45;
-}
+__device__ __forceinline__ int vertex_bucket(double x, int W) { return x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1); }
 
 template <bool SHARP>
 __device__ void polylines_eye(const RowSmem &sm, const NdSrc &nds, int W, double div_px, double sep_px, uint32_t dst_off, double *dbg) {
@@ -183,36 +178,48 @@ __device__ void polylines_eye(const RowSmem &sm, const NdSrc &nds, int W, double
     const bool fwd = !(div_px < 0.0);
     double *xs = sm.at<double>(sm.xs), *pm = sm.at<double>(sm.pm);
     uint16_t *order = sm.at<uint16_t>(sm.order);
+    uint16_t *rk = sm.at<uint16_t>(sm.pm);          // rank inside the bucket; lives in pm's memory until pm is built
     int *off = sm.at<int>(sm.off);
-    const uint8_t *src = sm.at<uint8_t>(sm.src);
+    const uint32_t *src = sm.at<uint32_t>(sm.src);
     uint8_t *dst = sm.at<uint8_t>(dst_off);
 
-    // 1. vertex x (kept in smem: every later phase reads it), bucket counters
-    for (int t = tid; t < n; t += T_) { const double x = vertex_x<SHARP>(t, n, W, nds, div_px, sep_px); xs[t] = x; pm[t] = x; }
+    // 1. vertex x (:177-192), one source pixel per thread iteration: both vertices of a sharp pixel share nd ** e * div_px.
+    //    The counting sort's histogram is taken on the way: atomicAdd returns the vertex's rank inside its bucket.
     for (int b = tid; b < W + 3; b += T_) off[b] = 0;
     __syncthreads();
-    // 2. counting sort by bucket(x): 0 for x<0, 1+floor(x) for 0<=x<W, W+1 for x>=W   (vertices 0..n-2 only, :214)
-    for (int t = tid; t < n - 1; t += T_) {
-        const double x = xs[t];
-        const int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
-        atomicAdd(&off[b], 1);
+    for (int col = tid; col < W; col += T_) {
+        const double coord_d = nds.get(col) * div_px;
+        const double coord_x = (double)col + 0.5 + coord_d + sep_px;
+        if (SHARP) {
+            const double xa = coord_x - 0.45, xb = coord_x + 0.45;
+            xs[1 + 2 * col] = xa; xs[2 + 2 * col] = xb;
+            rk[1 + 2 * col] = (uint16_t)atomicAdd(&off[vertex_bucket(xa, W)], 1);
+            rk[2 + 2 * col] = (uint16_t)atomicAdd(&off[vertex_bucket(xb, W)], 1);
+        } else {
+            xs[1 + col] = coord_x;
+            rk[1 + col] = (uint16_t)atomicAdd(&off[vertex_bucket(coord_x, W)], 1);
+        }
     }
+    if (tid == 0) {
+        xs[0] = -1.0 * (double)W; xs[n - 1] = 2.0 * (double)W;       // sentinels; the closing one never moves (:214)
+        rk[0] = (uint16_t)atomicAdd(&off[0], 1);
+    }
+    __syncthreads();
+    // 2. bucket ends (inclusive scan): afterwards off[b] = END of bucket b = START of bucket b + 1
+    block_scan_inclusive<int>(off, W + 2, 0, OpAddI(), false, sm.at<int>(sm.wtot_i));
+    for (int t = tid; t < n - 1; t += T_) {
+        const int b = vertex_bucket(xs[t], W);
+        order[(b ? off[b - 1] : 0) + (int)rk[t]] = (uint16_t)t;
+    }
+    if (tid == 0) order[n - 1] = (uint16_t)(n - 1);
+    __syncthreads();
+    // 3. prefix max / suffix min of x in ORIGINAL order (the rank array is dead now) and the order inside buckets by (x, index)
+    for (int t = tid; t < n; t += T_) pm[t] = xs[t];
     __syncthreads();
     if (fwd) block_scan_inclusive<double>(pm, n, -INFINITY, OpMaxD(), false, sm.at<double>(sm.wtot_d));
     else block_scan_inclusive<double>(pm, n, INFINITY, OpMinD(), true, sm.at<double>(sm.wtot_d));
-    block_scan_inclusive<int>(off, W + 2, 0, OpAddI(), false, sm.at<int>(sm.wtot_i));  // inclusive: off[b] = end of bucket b
-    // scatter by filling every bucket from its end backwards: no cursor array, and afterwards off[b] = START of bucket b
-    // (== end of bucket b-1); off[W+2] is set to n-1 so that "end of bucket b" is always off[b+1]
-    for (int t = tid; t < n - 1; t += T_) {
-        const double x = xs[t];
-        const int b = x < 0.0 ? 0 : (x >= (double)W ? W + 1 : (int)x + 1);
-        order[atomicSub(&off[b], 1) - 1] = (uint16_t)t;
-    }
-    if (tid == 0) { order[n - 1] = (uint16_t)(n - 1); off[W + 2] = n - 1; }
-    __syncthreads();
-    // 3. order inside buckets by (x, original index)
     for (int b = tid; b < W + 2; b += T_) {
-        const int beg = off[b], end = off[b + 1];
+        const int beg = b ? off[b - 1] : 0, end = off[b];
         if (end - beg < 2) continue;
         if (b == 0 || b == W + 1) {
             // bucket 0: only its maximum matters (predecessor of pixel 0) -> move it last;
@@ -246,12 +253,12 @@ __device__ void polylines_eye(const RowSmem &sm, const NdSrc &nds, int W, double
     if (dbg && tid == 0) {
         dbg[0] = n;
         for (int t = 0; t < n; ++t) { dbg[1 + t] = pm[t]; dbg[1 + n + t] = order[t]; dbg[1 + 2 * n + t] = xs[t]; }
-        for (int b = 0; b < W + 2; ++b) dbg[1 + 3 * n + b] = off[b + 1];
+        for (int b = 0; b < W + 2; ++b) dbg[1 + 3 * n + b] = off[b];
     }
     // 4. rasterise: one output pixel per thread iteration (:228-281)
     for (int col = tid; col < W; col += T_) {
         double c0 = 0.5, c1 = 0.5, c2 = 0.5;
-        int i = off[col + 1] - 1;  // last vertex with x < col  (start of bucket col+1 == number of vertices with x < col)
+        int i = off[col] - 1;  // last vertex with x < col  (end of bucket col == number of vertices with x < col)
         int ti = order[i];
         double xi = xs[ti];
         const double colf = (double)col, colp = (double)(col + 1);
@@ -294,19 +301,19 @@ __device__ void polylines_eye(const RowSmem &sm, const NdSrc &nds, int W, double
             int col_r = SHARP ? (s >> 1) : s;               // vertex n-1 (closing sentinel) -> W -> column W-1
             col_l = col_l < 0 ? 0 : (col_l > W - 1 ? W - 1 : col_l);
             col_r = col_r < 0 ? 0 : (col_r > W - 1 ? W - 1 : col_r);
-            const uint8_t *pl = src + 3 * col_l;
+            const uint32_t pl = src[col_l];
             if (col_l == col_r) {
-                c0 += (double)pl[0] * significance;
-                c1 += (double)pl[1] * significance;
-                c2 += (double)pl[2] * significance;
+                c0 += (double)(pl & 0xffu) * significance;
+                c1 += (double)((pl >> 8) & 0xffu) * significance;
+                c2 += (double)((pl >> 16) & 0xffu) * significance;
             } else {
-                const uint8_t *pr = src + 3 * col_r;
+                const uint32_t pr = src[col_r];
                 const double x0 = xs[s], x1 = xs[s + 1];
                 const double ip_k = (coord_center - x0) / (x1 - x0);
                 const double om = 1.0 - ip_k;
-                c0 += ((double)pl[0] * om + (double)pr[0] * ip_k) * significance;
-                c1 += ((double)pl[1] * om + (double)pr[1] * ip_k) * significance;
-                c2 += ((double)pl[2] * om + (double)pr[2] * ip_k) * significance;
+                c0 += ((double)(pl & 0xffu) * om + (double)(pr & 0xffu) * ip_k) * significance;
+                c1 += ((double)((pl >> 8) & 0xffu) * om + (double)((pr >> 8) & 0xffu) * ip_k) * significance;
+                c2 += ((double)((pl >> 16) & 0xffu) * om + (double)((pr >> 16) & 0xffu) * ip_k) * significance;
             }
             ++i;
             ti = tn;
@@ -424,10 +431,13 @@ __global__ void __launch_bounds__(256, POLY ? 2 : 4) stereo_row_kernel(StereoArg
     sm.cur = carve(a.fill == DM_FILL_NAIVE_INTERPOLATING ? sizeof(int) * (W + 3) : 16);
     sm.aux = carve(a.fill == DM_FILL_NAIVE_INTERPOLATING ? sizeof(int) * (W + 1) : 16);
     sm.order = carve(poly ? sizeof(uint16_t) * n : 16);
-    sm.src = carve((size_t)3 * W);
+    sm.src = carve(poly ? (size_t)4 * W : (size_t)3 * W);
     sm.eye[0] = carve((size_t)3 * W);
     sm.eye[1] = carve((size_t)3 * W);
-    uint8_t *s_src = sm.at<uint8_t>(sm.src);
+    // the naive family reads the row as bytes; polylines reads whole pixels (R | G << 8 | B << 16): the raw bytes land in the
+    // left-eye staging row first and are packed from there
+    uint8_t *s_src = sm.at<uint8_t>(poly ? sm.eye[0] : sm.src);
+    uint32_t *s_px = sm.at<uint32_t>(sm.src);
 
     // ---- load the row: RGB bytes and nd ** exponent --------------------------------------------------------
     const uint8_t *src_g = a.rgb + ((int64_t)b * a.H + y) * (int64_t)W * 3;
@@ -446,16 +456,20 @@ __global__ void __launch_bounds__(256, POLY ? 2 : 4) stereo_row_kernel(StereoArg
         }
         for (int i = h + nvec * 16 + tid; i < nbytes; i += T_) s_src[i] = __ldg(src_g + i);
     }
+    if (POLY) {
+        __syncthreads();
+        for (int c = tid; c < W; c += T_) s_px[c] = (uint32_t)s_src[3 * c] | ((uint32_t)s_src[3 * c + 1] << 8) | ((uint32_t)s_src[3 * c + 2] << 16);
+    }
     bool flat = false;
     NdSrc nds;
-    nds.ndp = nullptr; nds.dep = nullptr; nds.mn = 0; nds.den = 1.0; nds.expo = a.exponent; nds.pow_kind = pow_kind;
+    nds.ndp = nullptr; nds.dep = nullptr; nds.mn = 0; nds.den = 1.0; nds.rden = 1.0; nds.expo = a.exponent; nds.pow_kind = pow_kind;
     if (u16) {
         const uint16_t *dep = (const uint16_t *)a.depth + ((int64_t)b * a.H + y) * (int64_t)W;
         const uint32_t mn = a.minmax[2 * b], mx = a.minmax[2 * b + 1];
         flat = (mx == mn);
         uint16_t *s_dep = sm.at<uint16_t>(sm.ndp);
         for (int c = tid; c < W; c += T_) s_dep[c] = __ldg(dep + c);
-        nds.dep = s_dep; nds.mn = mn; nds.den = (double)(mx - mn);   // :81 (d - min) / (max - min), float64 true-divide
+        nds.dep = s_dep; nds.mn = mn; nds.den = (double)(mx - mn); nds.rden = 1.0 / nds.den;   // :81 (d - min) / (max - min), float64 true-divide
     } else {
         const double *dep = (const double *)a.depth + ((int64_t)b * a.H + y) * (int64_t)W;
         double *s_ndp = sm.at<double>(sm.ndp);
@@ -470,13 +484,14 @@ __global__ void __launch_bounds__(256, POLY ? 2 : 4) stereo_row_kernel(StereoArg
         const uint32_t dst_off = e == 0 ? sm.eye[0] : sm.eye[1];
         uint8_t *dst = sm.at<uint8_t>(dst_off);
         if (a.eye_mode[e] == DM_EYE_IDENTITY) {
-            for (int i = tid; i < 3 * W; i += T_) dst[i] = s_src[i];
+            if (POLY) { for (int i = tid; i < 3 * W; i += T_) dst[i] = (uint8_t)(s_px[i / 3] >> (8 * (i % 3))); }
+            else { for (int i = tid; i < 3 * W; i += T_) dst[i] = s_src[i]; }
             __syncthreads();
         } else if (flat) {
             // max == min: nd is 0/0 = NaN everywhere.  Reference behaviour (pinned by the oracle): the naive family
             // scatters nothing (black row); polylines degenerates to the first pixel's colour across the row.
             for (int c = tid; c < W; c += T_)
-                for (int k = 0; k < 3; ++k) dst[3 * c + k] = poly ? s_src[k] : (uint8_t)0;
+                for (int k = 0; k < 3; ++k) dst[3 * c + k] = poly ? (uint8_t)(s_px[0] >> (8 * k)) : (uint8_t)0;
             __syncthreads();
         } else if (POLY) {
             if (a.fill == DM_FILL_POLYLINES_SHARP)
@@ -491,7 +506,7 @@ __global__ void __launch_bounds__(256, POLY ? 2 : 4) stereo_row_kernel(StereoArg
     // ---- pack + store -------------------------------------------------------------------------------------------
     if (a.pack == DM_PACK_ANAGLYPH) {
         const uint8_t *er = sm.at<uint8_t>(a.red_eye ? sm.eye[1] : sm.eye[0]), *ec = sm.at<uint8_t>(a.red_eye ? sm.eye[0] : sm.eye[1]);
-        uint8_t *comp = s_src;
+        uint8_t *comp = sm.at<uint8_t>(sm.src);      // the source row is dead by now
         __syncthreads();
         for (int c = tid; c < W; c += T_) { comp[3 * c] = er[3 * c]; comp[3 * c + 1] = ec[3 * c + 1]; comp[3 * c + 2] = ec[3 * c + 2]; }
         __syncthreads();
@@ -549,7 +564,7 @@ static size_t stereo_smem_bytes(int W, int fill, int depth_kind) {
     const bool interp = fill == DM_FILL_NAIVE_INTERPOLATING;
     size_t s = r16(32 * 8) + r16(32 * 4) + r16((depth_kind == DM_DEPTH_U16 ? 2 : 8) * (size_t)W) + r16(poly ? 8 * n : 16) +
                r16(poly ? 8 * n : 3 * (size_t)W) + r16(4 * ((size_t)W + 4)) + r16(interp ? 4 * ((size_t)W + 3) : 16) +
-               r16(interp ? 4 * ((size_t)W + 1) : 16) + r16(poly ? 2 * n : 16) + 3 * r16(3 * (size_t)W);
+               r16(interp ? 4 * ((size_t)W + 1) : 16) + r16(poly ? 2 * n : 16) + r16(poly ? 4 * (size_t)W : 3 * (size_t)W) + 2 * r16(3 * (size_t)W);
     return s;
 }
 

@@ -266,16 +266,12 @@ class DepthAnythingV2Engine:
         pe = self._pos_embed
         C = pe.shape[-1]
         N = pe.shape[1] - 1
-        if gh * gw == N and gh == gw:
-            out = pe.reshape(N + 1, C).contiguous()
-        else:
-            sqrt_n = math.sqrt(N)
-            # the reference hands (w, h) = (tensor H, tensor W) to the function: "w0" follows the tensor height
-            w0, h0 = gh + 0.1, gw + 0.1
-            pp = F.interpolate(pe[:, 1:].reshape(1, int(sqrt_n), int(sqrt_n), C).permute(0, 3, 1, 2),
-                               scale_factor=(float(w0) / sqrt_n, float(h0) / sqrt_n), mode="bicubic", antialias=False)
-            assert pp.shape[-2] == gh and pp.shape[-1] == gw
-            out = torch.cat((pe[:, 0], pp.permute(0, 2, 3, 1).reshape(-1, C)), dim=0).contiguous()
+        n = int(round(math.sqrt(N)))
+        # host arithmetic shared with the model-level C-ABI (csrc/model.cu), so both paths use bit-identical tables
+        src = np.ascontiguousarray(pe.reshape(N + 1, C).cpu().numpy(), dtype=np.float32)
+        dst = np.empty((gh * gw + 1, C), dtype=np.float32)
+        _lib.check(self.ops.L.dm_dinov2_pos_embed(src.ctypes.data, n, C, gh, gw, dst.ctypes.data), "dm_dinov2_pos_embed")
+        out = torch.from_numpy(dst).to(self.device)
         self._pos_cache[key] = out
         return out
 
@@ -333,6 +329,18 @@ class DepthAnythingV2Engine:
     def attention(self, i, b, B, N, heads, C, gh, gw):
         self.ops.attention(b['qkv'], B, N, heads, (C // heads) ** -0.5, b['att'])
 
+    def _probed_attention(self, i, b, B, N, heads, C, gh, gw):
+        """bench hook: probe['attn'] collects one (start, end) CUDA event pair per attention launch"""
+        if self.probe is not None and 'attn' in self.probe:
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.attention(i, b, B, N, heads, C, gh, gw)
+            e1.record()
+            self.probe['attn'].append((e0, e1))
+        else:
+            self.attention(i, b, B, N, heads, C, gh, gw)
+
     def emit_feature(self, b, fi, B, N, C):
         """get_intermediate_layers(norm=True) without the class token (dinov2.py:297-321)."""
         self.ops.layernorm(b['x'], B * N, C, self.w['norm_w'], self.w['norm_b'], b['feat'][fi], tokens_per_img=N, drop_first=1)
@@ -371,13 +379,13 @@ class DepthAnythingV2Engine:
         for i, blk in enumerate(w['blocks']):
             ops.layernorm(b['x'], rows, C, blk['ln1_w'], blk['ln1_b'], b['h'])
             ops.gemm(b['h'], C, blk['qkv_w'], C, rows, 3 * C, C, bias=blk['qkv_b'], C=b['qkv'], ldc=3 * C)
-            self.attention(i, b, B, N, heads, C, gh, gw)
+            self._probed_attention(i, b, B, N, heads, C, gh, gw)
             ops.gemm(b['att'], C, blk['proj_w'], C, rows, C, C, epi=E.EPI_RESID_F32, bias=blk['proj_b'], X=b['x'], ldx=C, gamma=blk['ls1'])
             ops.layernorm(b['x'], rows, C, blk['ln2_w'], blk['ln2_b'], b['h'])
-            if self.probe is not None and i == 0:
+            if self.probe is not None and 'fc1' in self.probe and i == 0:
                 self.probe['fc1'][0].record()
             ops.gemm(b['h'], C, blk['fc1_w'], C, rows, 4 * C, C, act=A.ACT_GELU, bias=blk['fc1_b'], C=b['mlp'], ldc=4 * C)
-            if self.probe is not None and i == 0:
+            if self.probe is not None and 'fc1' in self.probe and i == 0:
                 self.probe['fc1'][1].record()
             ops.gemm(b['mlp'], 4 * C, blk['fc2_w'], 4 * C, rows, C, 4 * C, epi=E.EPI_RESID_F32, bias=blk['fc2_b'], X=b['x'], ldx=C, gamma=blk['ls2'])
             if i in cfg['layers']:
@@ -558,13 +566,15 @@ class DptBeitEngine(DepthAnythingV2Engine):
             new_h, new_w = 2 * gh - 1, 2 * gw - 1
             out = []
             idx = _gen_relative_position_index(gh, gw).to(self.device)       # [N, N]
+            nrd_new = new_h * new_w + 3
+            heads = self.cfg['heads']
             for t in self._tables:
-                sub = t[:old_h * old_w].reshape(1, old_w, old_h, -1).permute(0, 3, 1, 2)
-                new_sub = F.interpolate(sub, size=(int(new_h), int(new_w)), mode="bilinear")
-                new_sub = new_sub.permute(0, 2, 3, 1).reshape(new_h * new_w, -1)
-                table = torch.cat([new_sub, t[old_h * old_w:]])              # [nrd_new, heads]
-                tab = (table.t().contiguous() * 1.4426950408889634).float().contiguous()   # [heads, nrd]
-                # per (head, query) maximum of the bias over all keys: the kernel's row-max upper bound
+                # host arithmetic shared with the model-level C-ABI (csrc/model.cu: beit_rel_table_host)
+                src = np.ascontiguousarray(t.cpu().numpy(), dtype=np.float32)
+                dst = np.empty((heads, nrd_new), dtype=np.float32)
+                _lib.check(self.ops.L.dm_beit_rel_table(src.ctypes.data, win, heads, gh, gw, dst.ctypes.data), "dm_beit_rel_table")
+                tab = torch.from_numpy(dst).to(self.device)
+                # per (head, query) maximum of the bias over all keys: the round-1 kernel's row-max upper bound
                 rowmax = torch.stack([tab[hh][idx].max(dim=1).values for hh in range(tab.shape[0])]).contiguous()
                 out.append((tab, rowmax))
             self._bias_cache = {key: (out, new_h * new_w + 3)}  # keep one resolution resident (drops dense tables too)
@@ -973,6 +983,12 @@ class ModelHolder:
             raise NotImplementedError("BOOST is not implemented in depthmap_b200 yet (SURVEY.md §8 row D9)")
         if tiling_mode:
             raise NotImplementedError("tiling_mode (circular conv padding) is not implemented in depthmap_b200 yet")
+        if getattr(self, "no_half", False):
+            # reference: `no_half` keeps the network in fp32 (src/depthmap_generation.py:268-275).  The B200 path feeds the tensor
+            # cores fp16 operands (fp32 accumulation, fp32 residual stream) and has no fp32-operand variant: say so instead of
+            # silently ignoring the setting
+            raise NotImplementedError("no_half (fp32 network) is not implemented in depthmap_b200: the tensor-core path uses fp16 operands "
+                                      "with fp32 accumulation; unset the setting")
         if model_type in (12, 13, 14):
             letter = {12: 's', 13: 'b', 14: 'l'}[model_type]
             if self.weights_provider is not None:

@@ -60,3 +60,37 @@ def test_all_gather_batch_world2(n_items):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _video_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from depthmap_b200.dist import shard_range
+    from depthmap_b200.video_mode import exchange_halo, halo_plan
+    n_total = 5                                     # rank 0: frames 0-2, rank 1: frames 3-4 (and a 1-frame block case below)
+    frames = torch.arange(n_total * 6, dtype=torch.float32).reshape(n_total, 2, 3)
+    ok = True
+    for total in (5, 3):
+        lo, hi = shard_range(total, rank, world)
+        before, after = exchange_halo(frames[lo:hi].clone(), None, lo, total)
+        bi, ai = halo_plan(lo, hi - lo, total)
+        ok = ok and before.shape[0] == len(bi) and after.shape[0] == len(ai)
+        ok = ok and all(torch.equal(before[k], frames[g]) for k, g in enumerate(bi)) and all(torch.equal(after[k], frames[g]) for k, g in enumerate(ai))
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_video_halo_exchange_world2():
+    """sharded video normalisation: every rank ends up with the (at most two) frames before and after its block"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_video_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
