@@ -6,8 +6,11 @@ Prints ONE JSON line (rank 0).  A "step" = one pass of the hot path over one bat
 Workloads (BASELINE.json configs):
   depth_beit512     dpt_beit_large_512 @512x512, batch 32/GPU, depth only            (configs[1], the default once built)
   dav2_stereo       depth_anything_v2 vitl @518 + SBS stereo (polylines) + normal map (configs[2])
+  zoedepth_nk768    zoedepth_nk @768 (pad + flip TTA, 64 core forwards) + red-cyan anaglyph, batch 32/GPU (configs[3])
   stereo2048        normalise -> stereo SBS (div 2.5, polylines_sharp) -> normal map on 2048x2048, batch 16/GPU
                     (north_star's "2048x2048 stereo warp" HBM-roofline target)
+The default run (depth_beit512) carries the other three as `sub_benchmarks`, so one driver run covers BASELINE's
+"depth+stereo 512^2 & 2048^2"; `e2e_funnel` is the same workload through core_generation_funnel with PIL images in and out.
 
 `value` = images/s with inputs resident in HBM; `e2e` = same through the public batched API from pinned HOST buffers,
 H2D and D2H inside the timed region; `roofline` = dominant kernel vs MEASURED_PEAKS.json; `cpu_baseline` = the oracle
@@ -387,9 +390,11 @@ def measure(wl, args, world, dev, rank, local_rank, peaks, steps, with_cpu_basel
     roofline = None
     if rank == 0:
         if hasattr(wl, "probe"):
-            roofline = wl.roofline_from_probe(peaks, wl.probe(3), ms_step)
+            roofline = wl.roofline_from_probe(peaks, wl.probe(20), ms_step)
         else:
             evs = []
+            wl.step_resident(True)                      # warm the eager path (allocator) before the measured launches
+            torch.cuda.synchronize()
             for _ in range(3):
                 wl.step_resident(True)
                 evs.append(wl._ev)
@@ -449,7 +454,7 @@ def measure(wl, args, world, dev, rank, local_rank, peaks, steps, with_cpu_basel
 
 
 # sub-benchmarks carried in the default run so that the driver's record covers BASELINE's "depth+stereo 512^2 & 2048^2"
-SUB_WORKLOADS = {"depth_beit512": ["stereo2048", "dav2_stereo"]}
+SUB_WORKLOADS = {"depth_beit512": ["stereo2048", "dav2_stereo", "zoedepth_nk768"]}
 
 
 def main():

@@ -20,34 +20,47 @@ class _NetWorkload:
     heads = 16
     C = 1024
 
-    def _probe_step(self, run_engine):
-        """one eager op-level forward with events around the attention launches and the block-0 fc1"""
+    def probe(self, n=20):
+        """Dominant-kernel timing, live in this run: the op-level engine runs one forward (so its buffers hold this workload's
+        real activations), then the fused attention kernel of the LAST block and the fc1 GEMM are launched n times back to back
+        on those buffers with CUDA events around the loop (GPU-bound: no host gaps inside the interval); the forward itself is
+        timed on the native model (the thing the timed region runs)."""
         import torch
-        self.engine.probe = {'attn': [], 'fc1': (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))}
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_engine()
-        e1.record()
-        pr, self.engine.probe = self.engine.probe, None
-        return pr, (e0, e1)
-
-    def probe(self, n=3):
-        """-> dict(attn_ms_per_launch, attn_launches, fc1_ms, forward_ms): mean over n eager op-level forwards"""
-        import torch
-        acc = []
-        for _ in range(n):
-            acc.append(self._probe_step(self._engine_forward))
+        from depthmap_b200 import _lib
+        eng = self.engine
+        for _ in range(2):
+            self._engine_forward()
         torch.cuda.synchronize()
-        attn = [np.mean([a.elapsed_time(b) for a, b in pr['attn']]) for pr, _ in acc]
-        fc1 = [pr['fc1'][0].elapsed_time(pr['fc1'][1]) for pr, _ in acc]
-        fwd = [a.elapsed_time(b) for _, (a, b) in acc]
-        return {"attn_ms_per_launch": float(np.mean(attn)), "attn_launches": len(acc[0][0]['attn']), "fc1_ms": float(np.mean(fc1)),
-                "forward_ms": float(np.mean(fwd))}
+        b = eng._bufs
+        cfg = eng.cfg
+        C, heads = cfg['embed_dim'], cfg['heads']
+        _, nh, nw = eng._buf_key
+        gh, gw = nh // eng.PATCH, nw // eng.PATCH
+        N = gh * gw + 1
+        last = cfg['depth'] - 1
+        blk = eng.w['blocks'][last]
+        PB = getattr(self, 'probe_batch', self.B)
+        rows = PB * N
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        attn_ms = timed(lambda: eng.attention(last, b, PB, N, heads, C, gh, gw))
+        fc1_ms = timed(lambda: eng.ops.gemm(b['h'], C, blk['fc1_w'], C, rows, 4 * C, C, act=_lib.ACT_GELU, bias=blk['fc1_b'], C=b['mlp'], ldc=4 * C))
+        fwd_ms = timed(self._model_forward)
+        return {"attn_ms_per_launch": float(attn_ms), "attn_launches": cfg['depth'], "fc1_ms": float(fc1_ms), "forward_ms": float(fwd_ms)}
 
     def roofline_from_probe(self, peaks, pr, ms_step):
         """Dominant kernel = the fused attention kernel (largest share of the step, measured here); fc1 reported beside it."""
         N = self.N
-        attn_flops = 4.0 * self.B * self.heads * N * N * 64          # QK^T + PV, 2 flops per MAC (SURVEY 8d: 2.15 + 2.15 GFLOP / image / block)
+        attn_flops = 4.0 * getattr(self, 'probe_batch', self.B) * self.heads * N * N * 64          # QK^T + PV, 2 flops per MAC (SURVEY 8d: 2.15 + 2.15 GFLOP / image / block)
         a = attn_flops / (pr["attn_ms_per_launch"] * 1e-3) / 1e12
         f = self.fc1_flops / (pr["fc1_ms"] * 1e-3) / 1e12
         share = pr["attn_ms_per_launch"] * pr["attn_launches"] / pr["forward_ms"]
@@ -55,9 +68,12 @@ class _NetWorkload:
                 "frac": a / peaks["bf16_tflops"], "traffic": None, "traffic_note": "see profiles/r02_ncu_attention_fwd4.txt (one ncu --set full capture per kernel)",
                 "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "algorithmic_flops_per_launch": attn_flops,
                 "kernel_ms": pr["attn_ms_per_launch"], "launches_per_step": pr["attn_launches"],
-                "share_of_step": share, "share_note": "sum of the attention launches / eager op-level forward, CUDA events, this run",
+                "share_of_step": share, "share_note": "attention launches per forward x kernel time / forward time of the model handle, all CUDA events, this run",
                 "secondary": {"kernel": self.FC1_KERNEL, "achieved": f, "frac": f / peaks["bf16_tflops"], "kernel_ms": pr["fc1_ms"],
                               "algorithmic_flops_per_launch": self.fc1_flops}}
+
+    def _model_forward(self):
+        return self.model.forward_batch(self.rgb, self.W, self.H)
 
     def extra(self, ms_step, peaks):
         fwd = self.FLOP_PER_IMAGE * self.B / (ms_step * 1e-3) / 1e12
@@ -264,6 +280,96 @@ class DepthBeit512(_NetWorkload):
         return 1, time.perf_counter() - t0
 
 
+class ZoeAnaglyph(_NetWorkload):
+    """BASELINE.json configs[3]: zoedepth_nk at 768x768 + anaglyph stereo, 32 images per GPU (256 over 8 GPUs, sharded, one
+    NCCL gather).  Every image runs twice through the DPT-BEiT-L-384 core (flip TTA): 64 forwards at the 512x512 net size
+    that PrepForMidas picks for the reflect-padded 884x884 input with the UI default net (w 384, h 512)."""
+    name = "zoedepth_nk768"
+    H = W = 768
+    B = 32
+    dtype = "fp16"
+    NET_W, NET_H = 384, 512
+    FLOP_PER_IMAGE = 2 * 962.7e9 + 2 * 10e9      # SURVEY 8d: two core forwards at 512x512 + the metric head (~1%)
+    ATTN_KERNEL = "attention_fwd4_kernel<3> (fused softmax(QK^T + rel-pos bias)V of the BEiT-L-384 core at a 32x32 window, 64 forwards)"
+    FC1_KERNEL = "gemm_tcgen05_2sm_kernel (block MLP fc1: M=64*1025, N=4096, K=1024, GELU epilogue)"
+
+    def _state_dict(self):
+        from oracle import beit_dpt, synth_weights
+        csd = synth_weights.make_beit_dpt_state_dict('beitl16_384', seed=0)
+        hsd = synth_weights.make_zoedepth_head_state_dict(feat_ch=beit_dpt.CONFIGS['beitl16_384']['features'], seed=100, gain=1.5)
+        sd = {"core.core." + k: v for k, v in csd.items()}
+        sd.update(hsd)
+        return sd
+
+    def funnel_options(self):
+        return dict(compute_device='GPU', model_type=9, net_width=self.NET_W, net_height=self.NET_H, do_output_depth=True, gen_stereo=True,
+                    stereo_modes=['red-cyan-anaglyph'], stereo_divergence=2.5, stereo_fill_algo='polylines_sharp')
+
+    def __init__(self, dev, rank):
+        import torch
+        from bench import make_images
+        from depthmap_b200.depthmap_generation import ZoeDepthNKEngine
+        self.dev = dev
+        self.engine = ZoeDepthNKEngine(self._state_dict(), dev)
+        self.model = self.engine
+        rgb, _ = make_images(self.B, self.H, self.W, rank)
+        self.rgb_h = torch.from_numpy(rgb).pin_memory()
+        self.rgb = self.rgb_h.to(dev)
+        self.probe_batch = 2 * self.B
+        self.N = 32 * 32 + 1
+        self.fc1_flops = 2.0 * self.probe_batch * self.N * 1024 * 4096
+        self.launches_per_step = None
+
+    def config(self):
+        return {"workload": "zoedepth_nk (DPT-BEiT-L-384 core + metric head, pad + flip TTA) 768x768 -> u16 depth -> red-cyan anaglyph "
+                            "(divergence 2.5, polylines_sharp)", "batch_per_gpu": self.B, "height": self.H, "width": self.W,
+                "net": "384x512 (UI default) -> 512x512 for the padded 884x884 input", "weights": "seeded synthetic, ZoeD_M12_NK checkpoint layout",
+                "l2_policy": "activations per step (>20 GB) far exceed the 126 MB L2"}
+
+    def step(self, rgb, time_kernel=False):
+        from depthmap_b200.core import normalize_prediction_batch
+        from depthmap_b200.stereoimage_generation import create_stereoimages_batch
+        n0 = self.engine.ops.launches
+        pred = self.engine.forward_batch(rgb, self.NET_W, self.NET_H)
+        depth = normalize_prediction_batch(pred, True)
+        ana = create_stereoimages_batch(rgb, depth, 2.5, 0.0, ['red-cyan-anaglyph'], 0.0, 1.0, 'polylines_sharp')[0]
+        self.launches_per_step = (self.engine.ops.launches - n0) + 3 + 3
+        return depth, ana
+
+    def step_resident(self, time_kernel=False):
+        return self.step(self.rgb, time_kernel)
+
+    def step_e2e(self):
+        rgb = self.rgb_h.to(self.dev, non_blocking=True)
+        outs = self.step(rgb)
+        return [o.to("cpu", non_blocking=True) for o in outs]
+
+    def e2e_bytes(self):
+        return self.rgb_h.numel(), self.B * self.H * self.W * (2 + 3)
+
+    def _engine_forward(self):
+        return self.engine.forward_batch(self.rgb, self.NET_W, self.NET_H)
+
+    def _model_forward(self):
+        return self.engine.forward_batch(self.rgb, self.NET_W, self.NET_H)
+
+    def cpu_sample(self, nthreads):
+        """reference CPU path on one image: fp32 torch ZoeDepth-NK (oracle restatement, 2 core forwards) + C oracle normalise / stereo."""
+        import torch
+        from oracle import normalmap as onm
+        from oracle import stereo as ost
+        from oracle import zoedepth as ozd
+        if not hasattr(self, "_sd_cpu"):
+            self._sd_cpu = self._state_dict()
+        rgb = self.rgb_h[0].numpy()
+        torch.set_num_threads(nthreads)
+        t0 = time.perf_counter()
+        pred, inv = ozd.get_raw_prediction(rgb, self._sd_cpu, self.NET_W, self.NET_H, core_name='beitl16_384')
+        d = onm.normalize_to_u16(pred, inv)
+        ost.create_stereoimages(rgb, d, 2.5, 0.0, ['red-cyan-anaglyph'], 0.0, 1.0, 'polylines_sharp', return_arrays=True, nthreads=nthreads)
+        return 1, time.perf_counter() - t0
+
+
 class Dav2StereoSmall(Dav2Stereo):
     """ViT-S variant for quick functional runs."""
     name = "dav2s_stereo"
@@ -274,4 +380,4 @@ class Dav2StereoSmall(Dav2Stereo):
     heads, C = 6, 384
 
 
-MODEL_WORKLOADS = {"depth_beit512": DepthBeit512, "dav2_stereo": Dav2Stereo, "dav2s_stereo": Dav2StereoSmall}
+MODEL_WORKLOADS = {"depth_beit512": DepthBeit512, "dav2_stereo": Dav2Stereo, "dav2s_stereo": Dav2StereoSmall, "zoedepth_nk768": ZoeAnaglyph}

@@ -28,6 +28,13 @@ CONFIGS = {
     # small test-only configuration with the same structure
     'beit_tiny': dict(embed_dim=128, depth=4, heads=2, features=64, out_channels=[64, 64, 128, 128],
                       hooks=[0, 1, 2, 3], window=4, net=64),
+    # MiDaS 3.0 dpt_large_384 (model type 3): timm vit_large_patch16_384 driven by the reference's forward_flex
+    # (dmidas/backbones/vit.py:12-79,107-118): absolute position embedding (bilinear resize of the 24x24 grid), no relative
+    # position bias, no LayerScale, qkv with a full bias; same hooks / readout / decoder as the BEiT models
+    'vitl16_384': dict(embed_dim=1024, depth=24, heads=16, features=256, out_channels=[256, 512, 1024, 1024],
+                       hooks=[5, 11, 17, 23], window=24, net=384, family='vit'),
+    'vit_tiny': dict(embed_dim=128, depth=4, heads=2, features=64, out_channels=[64, 64, 128, 128],
+                     hooks=[0, 1, 2, 3], window=4, net=64, family='vit'),
 }
 
 
@@ -129,6 +136,44 @@ def backbone_hooks(sd, x, cfg):
     return outs
 
 
+def vit_resize_pos_embed(posemb, gs_h, gs_w):
+    """dmidas/backbones/vit.py:16-31 (_resize_pos_embed, start_index 1): bilinear, align_corners=False."""
+    tok, grid = posemb[:, :1], posemb[0, 1:]
+    gs_old = int(np.sqrt(len(grid)))
+    grid = grid.reshape(1, gs_old, gs_old, -1).permute(0, 3, 1, 2)
+    grid = F.interpolate(grid, size=(gs_h, gs_w), mode="bilinear")
+    grid = grid.permute(0, 2, 3, 1).reshape(1, gs_h * gs_w, -1)
+    return torch.cat([tok, grid], dim=1)
+
+
+def vit_backbone_hooks(sd, x, cfg):
+    """forward_flex (dmidas/backbones/vit.py:34-79) over timm's VisionTransformer blocks (pre-norm, qkv with bias, GELU MLP,
+    LayerNorm eps 1e-6) with the four forward hooks; returns the raw block outputs [B, N, C]."""
+    B, _, H, W = x.shape
+    C, heads = cfg['embed_dim'], cfg['heads']
+    p = 'pretrained.model.'
+    pos = vit_resize_pos_embed(sd[p + 'pos_embed'].float(), H // 16, W // 16)
+    t = F.conv2d(x, sd[p + 'patch_embed.proj.weight'].float(), sd[p + 'patch_embed.proj.bias'].float(), stride=16)
+    t = t.flatten(2).transpose(1, 2)
+    t = torch.cat((sd[p + 'cls_token'].float().expand(B, -1, -1), t), dim=1) + pos
+    outs = []
+    for i in range(cfg['depth']):
+        b = p + f'blocks.{i}.'
+        h = F.layer_norm(t, (C,), sd[b + 'norm1.weight'].float(), sd[b + 'norm1.bias'].float(), 1e-6)
+        qkv = F.linear(h, sd[b + 'attn.qkv.weight'].float(), sd[b + 'attn.qkv.bias'].float())
+        N = t.shape[1]
+        q, k, v = qkv.reshape(B, N, 3, heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
+        attn = ((q * (C // heads) ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
+        o = (attn @ v).transpose(1, 2).reshape(B, N, -1)
+        t = t + F.linear(o, sd[b + 'attn.proj.weight'].float(), sd[b + 'attn.proj.bias'].float())
+        h = F.layer_norm(t, (C,), sd[b + 'norm2.weight'].float(), sd[b + 'norm2.bias'].float(), 1e-6)
+        h = F.gelu(F.linear(h, sd[b + 'mlp.fc1.weight'].float(), sd[b + 'mlp.fc1.bias'].float()))
+        t = t + F.linear(h, sd[b + 'mlp.fc2.weight'].float(), sd[b + 'mlp.fc2.bias'].float())
+        if i in cfg['hooks']:
+            outs.append(t)
+    return outs
+
+
 def _conv(sd, key, x, stride=1, padding=0):
     b = sd.get(key + '.bias')
     return F.conv2d(x, sd[key + '.weight'].float(), None if b is None else b.float(), stride=stride, padding=padding)
@@ -158,7 +203,7 @@ def forward(sd, x, name, return_features=False):
     cfg = CONFIGS[name]
     B, _, H, W = x.shape
     gh, gw = H // 16, W // 16
-    hooks = backbone_hooks(sd, x, cfg)
+    hooks = vit_backbone_hooks(sd, x, cfg) if cfg.get('family') == 'vit' else backbone_hooks(sd, x, cfg)
     layers = []
     for j, t in enumerate(hooks, start=1):
         a = f'pretrained.act_postprocess{j}.'
@@ -194,7 +239,7 @@ def forward(sd, x, name, return_features=False):
 
 @torch.no_grad()
 def get_raw_prediction(rgb_uint8, sd, name, net_w, net_h):
-    """ModelHolder.get_raw_prediction for model types 1 / 2 -> (float32 [H,W], invert=False)."""
+    """ModelHolder.get_raw_prediction for model types 1 / 2 / 3 -> (float32 [H,W], invert=False)."""
     img = np.asarray(rgb_uint8)
     x = preprocess(img, net_w, net_h)
     pred = forward(sd, x, name)

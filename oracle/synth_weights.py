@@ -91,23 +91,31 @@ def make_beit_dpt_state_dict(name='beit_tiny', seed=0, dtype=torch.float32):
     sd[p + 'patch_embed.proj.weight'] = rn(C, 3, 16, 16, std=(1.0 / 768) ** 0.5 * 2.0)
     sd[p + 'patch_embed.proj.bias'] = rn(C, std=0.02)
     nrd = (2 * win - 1) * (2 * win - 1) + 3
+    vit = cfg.get('family') == 'vit'
+    if vit:
+        sd[p + 'pos_embed'] = rn(1, win * win + 1, C, std=0.1)
+        sd[p + 'norm.weight'] = rn(C, std=0.05, mean=1.0)
+        sd[p + 'norm.bias'] = rn(C, std=0.02)
     for i in range(depth):
         b = p + f'blocks.{i}.'
-        sd[b + 'gamma_1'] = rn(C, std=0.02, mean=0.2)
-        sd[b + 'gamma_2'] = rn(C, std=0.02, mean=0.2)
         sd[b + 'norm1.weight'] = rn(C, std=0.05, mean=1.0)
         sd[b + 'norm1.bias'] = rn(C, std=0.02)
-        sd[b + 'attn.q_bias'] = rn(C, std=0.02)
-        sd[b + 'attn.v_bias'] = rn(C, std=0.02)
-        sd[b + 'attn.relative_position_bias_table'] = rn(nrd, heads, std=1.0)
+        if vit:     # no LayerScale: keep the residual branches small through the weights instead
+            sd[b + 'attn.qkv.bias'] = rn(3 * C, std=0.02)
+        else:
+            sd[b + 'gamma_1'] = rn(C, std=0.02, mean=0.2)
+            sd[b + 'gamma_2'] = rn(C, std=0.02, mean=0.2)
+            sd[b + 'attn.q_bias'] = rn(C, std=0.02)
+            sd[b + 'attn.v_bias'] = rn(C, std=0.02)
+            sd[b + 'attn.relative_position_bias_table'] = rn(nrd, heads, std=1.0)
         sd[b + 'attn.qkv.weight'] = rn(3 * C, C, std=C ** -0.5)
-        sd[b + 'attn.proj.weight'] = rn(C, C, std=C ** -0.5)
+        sd[b + 'attn.proj.weight'] = rn(C, C, std=C ** -0.5 * (0.2 if vit else 1.0))
         sd[b + 'attn.proj.bias'] = rn(C, std=0.02)
         sd[b + 'norm2.weight'] = rn(C, std=0.05, mean=1.0)
         sd[b + 'norm2.bias'] = rn(C, std=0.02)
         sd[b + 'mlp.fc1.weight'] = rn(4 * C, C, std=C ** -0.5)
         sd[b + 'mlp.fc1.bias'] = rn(4 * C, std=0.02)
-        sd[b + 'mlp.fc2.weight'] = rn(C, 4 * C, std=(4 * C) ** -0.5)
+        sd[b + 'mlp.fc2.weight'] = rn(C, 4 * C, std=(4 * C) ** -0.5 * (0.2 if vit else 1.0))
         sd[b + 'mlp.fc2.bias'] = rn(C, std=0.02)
     for j in range(1, 5):
         a = f'pretrained.act_postprocess{j}.'

@@ -1,0 +1,14 @@
+# ncu evidence for profiles/: the launch list of one eager step + one `--set full` capture per kernel family
+mkdir -p gpurun_out
+P="ncu --clock-control none --profile-from-start off"
+$P --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r02_launches_depth_beit512.csv python tools/profile_step.py depth_beit512 > gpurun_out/prof_launch_beit.log 2>&1
+$P --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r02_launches_dav2_stereo.csv python tools/profile_step.py dav2_stereo 16 > gpurun_out/prof_launch_dav2.log 2>&1
+F="$P --set full --import-source off -f"
+$F -k regex:attention_fwd4 -s 2 -c 1 -o gpurun_out/r02_attn python tools/profile_step.py depth_beit512 > gpurun_out/prof_a.log 2>&1
+$F -k regex:gemm_tcgen05_2sm_kernel -s 8 -c 8 -o gpurun_out/r02_gemm2sm python tools/profile_step.py depth_beit512 > gpurun_out/prof_b.log 2>&1
+$F -k "regex:gemm_tcgen05_kernel|gemm_tcgen05_persist" -c 6 -o gpurun_out/r02_gemm1 python tools/profile_step.py depth_beit512 > gpurun_out/prof_c.log 2>&1
+$F -k "regex:layernorm|preprocess|assemble|concat_readout|attention_cls_row|im2col" -s 6 -c 8 -o gpurun_out/r02_small python tools/profile_step.py depth_beit512 > gpurun_out/prof_d.log 2>&1
+$F -k "regex:resize|minmax_f32|quantize" -c 8 -o gpurun_out/r02_resize python tools/profile_step.py depth_beit512 > gpurun_out/prof_e.log 2>&1
+$F -k "regex:stereo_row|normalmap|minmax_u16" -c 3 -o gpurun_out/r02_stereo python tools/profile_step.py stereo2048 > gpurun_out/prof_f.log 2>&1
+$F -k regex:attention_fwd4 -s 2 -c 1 -o gpurun_out/r02_attn_dav2 python tools/profile_step.py dav2_stereo 16 > gpurun_out/prof_g.log 2>&1
+ls -la gpurun_out/*.ncu-rep | tail -12

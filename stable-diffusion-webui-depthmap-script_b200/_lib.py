@@ -76,7 +76,7 @@ EXPORTS = [
     "dm_resize_add_nhwc_f16", "dm_zoe_attractor", "dm_zoe_clb_final", "dm_zoe_tta_combine",
     "dm_video_workspace_bytes", "dm_video_blend", "dm_video_minmax", "dm_video_scale_f32", "dm_video_select_init", "dm_video_select_hist",
     "dm_video_select_pick", "dm_video_select_bounds", "dm_video_scale_f64",
-    "dm_model_create", "dm_model_destroy", "dm_model_net_size", "dm_model_launches", "dm_depth_forward", "dm_dinov2_pos_embed", "dm_beit_rel_table",
+    "dm_model_create", "dm_model_destroy", "dm_model_net_size", "dm_model_launches", "dm_depth_forward", "dm_dinov2_pos_embed", "dm_beit_rel_table", "dm_vit_pos_embed",
 ]
 
 
@@ -127,6 +127,7 @@ def load() -> ctypes.CDLL:
             L.dm_depth_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp]
             L.dm_dinov2_pos_embed.argtypes = [vp, i32, i32, i32, i32, vp]
             L.dm_beit_rel_table.argtypes = [vp, i32, i32, i32, i32, vp]
+            L.dm_vit_pos_embed.argtypes = [vp, i32, i32, i32, i32, vp]
         _bind_optional(L)
         _lib = L
         return L

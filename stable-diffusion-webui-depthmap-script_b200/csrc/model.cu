@@ -28,7 +28,7 @@ namespace dm {
 static int ru(int x, int m) { return (x + m - 1) / m * m; }
 
 struct ModelCfg {
-    int family;            // 0 = Depth-Anything-V2 (DINOv2 + DPT head), 1 = MiDaS 3.1 DPT-BEiT
+    int family;            // 0 = Depth-Anything-V2 (DINOv2 + DPT head), 1 = MiDaS 3.1 DPT-BEiT, 2 = MiDaS 3.0 DPT-ViT (dpt_large_384)
     int C, depth, heads, Fch, oc[4], layers[4], window, patch;
     float mean[3], stdv[3];
     int final_mode;        // dm_resize_f32 mode
@@ -50,7 +50,9 @@ static bool model_cfg(int model_type, ModelCfg &c) {
         case 14: set(0, 1024, 24, 16, 256, {256, 512, 1024, 1024}, {4, 11, 17, 23}, 0, 14, im_mean, im_std, 0, "depth_anything_v2_vitl"); return true;
         case 1: set(1, 1024, 24, 16, 256, {256, 512, 1024, 1024}, {5, 11, 17, 23}, 32, 16, half3, half3, 1, "dpt_beit_large_512"); return true;
         case 2: set(1, 1024, 24, 16, 256, {256, 512, 1024, 1024}, {5, 11, 17, 23}, 24, 16, half3, half3, 1, "dpt_beit_large_384"); return true;
+        case 3: set(2, 1024, 24, 16, 256, {256, 512, 1024, 1024}, {5, 11, 17, 23}, 24, 16, half3, half3, 1, "dpt_large_384"); return true;
         case -100: set(1, 128, 4, 2, 64, {64, 64, 128, 128}, {0, 1, 2, 3}, 4, 16, half3, half3, 1, "beit_tiny (structural test configuration)"); return true;
+        case -101: set(2, 128, 4, 2, 64, {64, 64, 128, 128}, {0, 1, 2, 3}, 4, 16, half3, half3, 1, "vit_tiny (structural test configuration)"); return true;
     }
     return false;
 }
@@ -177,8 +179,8 @@ static int pack_convT(dm_model *m, const Weights &W, const std::string &key, int
 static int pack_model(dm_model *m, const Weights &W) {
     const ModelCfg &c = m->cfg;
     const int C = c.C, Fch = c.Fch;
-    const bool beit = c.family == 1;
-    const std::string tp = beit ? "pretrained.model." : "pretrained.";
+    const bool beit = c.family == 1, vit = c.family == 2, midas = beit || vit;
+    const std::string tp = midas ? "pretrained.model." : "pretrained.";
     const int kraw = 3 * c.patch * c.patch;
     m->kpad = ru(kraw, 64);
     __half *h; float *f;
@@ -186,7 +188,7 @@ static int pack_model(dm_model *m, const Weights &W) {
     DM_TRY(pack_vec(m, W, tp + "patch_embed.proj.bias", C, C, &f)); m->w["pe_b"] = f;
     DM_TRY(pack_vec(m, W, tp + "cls_token", C, C, &f)); m->w["cls"] = f;
     if (!beit) {
-        const dm_weight *pe = W.find("pretrained.pos_embed");
+        const dm_weight *pe = W.find(tp + "pos_embed");
         if (!pe || pe->ndim < 2) { set_error("dm_model_create: pretrained.pos_embed missing"); return DM_E_INVALID; }
         const int64_t n = Weights::numel(pe);
         const int tokens = (int)(n / C);
@@ -218,19 +220,22 @@ static int pack_model(dm_model *m, const Weights &W) {
             if (!rt || Weights::numel(rt) != (int64_t)nrd0 * c.heads) { set_error("dm_model_create: %sattn.relative_position_bias_table missing or of unexpected size", p.c_str()); return DM_E_INVALID; }
             b.rel_table_host.resize((size_t)nrd0 * c.heads);
             for (size_t k = 0; k < b.rel_table_host.size(); ++k) b.rel_table_host[k] = Weights::at(rt, (int64_t)k);
+        } else if (vit) {      // timm VisionTransformer block: full qkv bias, no LayerScale
+            DM_TRY(pack_vec(m, W, p + "attn.qkv.bias", 3 * C, 3 * C, &b.qkv_b));
+            DM_TRY(const_vec(m, 1.f, C, &b.ls1)); DM_TRY(const_vec(m, 1.f, C, &b.ls2));
         } else {
             DM_TRY(pack_vec(m, W, p + "attn.qkv.bias", 3 * C, 3 * C, &b.qkv_b));
             DM_TRY(pack_vec(m, W, p + "ls1.gamma", C, C, &b.ls1)); DM_TRY(pack_vec(m, W, p + "ls2.gamma", C, C, &b.ls2));
         }
     }
-    if (beit) { DM_TRY(const_vec(m, 1.f, C, &f)); m->w["norm_w"] = f; DM_TRY(const_vec(m, 0.f, C, &f)); m->w["norm_b"] = f; }
+    if (midas) { DM_TRY(const_vec(m, 1.f, C, &f)); m->w["norm_w"] = f; DM_TRY(const_vec(m, 0.f, C, &f)); m->w["norm_b"] = f; }   // hooks read raw block outputs
     else { DM_TRY(pack_vec(m, W, "pretrained.norm.weight", C, C, &f)); m->w["norm_w"] = f; DM_TRY(pack_vec(m, W, "pretrained.norm.bias", C, C, &f)); m->w["norm_b"] = f; }
     // ---- reassemble + DPT decoder; channel counts padded to multiples of 64 with zero weights ----
     for (int i = 0; i < 4; ++i) m->ocp[i] = ru(c.oc[i], 64);
     m->Fp = ru(Fch, 64); m->F2p = ru(Fch / 2, 64);
-    auto key_proj = [&](int i, const char *wb) { return beit ? "pretrained.act_postprocess" + std::to_string(i + 1) + ".3." + wb : "depth_head.projects." + std::to_string(i) + "." + wb; };
-    auto key_resize = [&](int i, const char *wb) { return beit ? "pretrained.act_postprocess" + std::to_string(i + 1) + ".4." + wb : "depth_head.resize_layers." + std::to_string(i) + "." + wb; };
-    const std::string sc = beit ? "scratch." : "depth_head.scratch.";
+    auto key_proj = [&](int i, const char *wb) { return midas ? "pretrained.act_postprocess" + std::to_string(i + 1) + ".3." + wb : "depth_head.projects." + std::to_string(i) + "." + wb; };
+    auto key_resize = [&](int i, const char *wb) { return midas ? "pretrained.act_postprocess" + std::to_string(i + 1) + ".4." + wb : "depth_head.resize_layers." + std::to_string(i) + "." + wb; };
+    const std::string sc = midas ? "scratch." : "depth_head.scratch.";
     for (int i = 0; i < 4; ++i) {
         DM_TRY(pack_mat(m, W, key_proj(i, "weight"), c.oc[i], C, m->ocp[i], C, &h)); m->w["proj" + std::to_string(i) + "_w"] = h;
         DM_TRY(pack_vec(m, W, key_proj(i, "bias"), c.oc[i], m->ocp[i], &f)); m->w["proj" + std::to_string(i) + "_b"] = f;
@@ -256,9 +261,9 @@ static int pack_model(dm_model *m, const Weights &W) {
                 DM_TRY(pack_vec(m, W, k + "bias", Fch, m->Fp, &f)); m->w[rk2 + "_b"] = f;
             }
     }
-    const std::string oc1 = beit ? "scratch.output_conv.0." : "depth_head.scratch.output_conv1.";
-    const std::string oc2 = beit ? "scratch.output_conv.2." : "depth_head.scratch.output_conv2.0.";
-    const std::string oc3 = beit ? "scratch.output_conv.4." : "depth_head.scratch.output_conv2.2.";
+    const std::string oc1 = midas ? "scratch.output_conv.0." : "depth_head.scratch.output_conv1.";
+    const std::string oc2 = midas ? "scratch.output_conv.2." : "depth_head.scratch.output_conv2.0.";
+    const std::string oc3 = midas ? "scratch.output_conv.4." : "depth_head.scratch.output_conv2.2.";
     DM_TRY(pack_conv3(m, W, oc1 + "weight", Fch / 2, Fch, m->F2p, m->Fp, &h)); m->w["oc1_w"] = h;
     DM_TRY(pack_vec(m, W, oc1 + "bias", Fch / 2, m->F2p, &f)); m->w["oc1_b"] = f;
     DM_TRY(pack_conv3(m, W, oc2 + "weight", 32, Fch / 2, 32, m->F2p, &h)); m->w["oc2_w"] = h;
@@ -267,7 +272,7 @@ static int pack_model(dm_model *m, const Weights &W) {
     const dm_weight *b3 = W.find(oc3 + "bias");
     if (!b3) { set_error("dm_model_create: %sbias missing", oc3.c_str()); return DM_E_INVALID; }
     m->oc3_b = Weights::at(b3, 0);
-    if (beit)
+    if (midas)
         for (int j = 0; j < 4; ++j) {
             const std::string a = "pretrained.act_postprocess" + std::to_string(j + 1) + ".0.project.0.";
             DM_TRY(pack_mat(m, W, a + "weight", C, 2 * C, C, 2 * C, &h)); m->w["ro" + std::to_string(j) + "_w"] = h;
@@ -350,6 +355,19 @@ static void cubic_w(float x, float *c) {
     c[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
     c[3] = ((A * (2.f - x) - 5.f * A) * (2.f - x) + 8.f * A) * (2.f - x) - 4.f * A;
 }
+// MiDaS 3.0 _resize_pos_embed (dmidas/backbones/vit.py:16-31): class entry kept, the n x n grid resized bilinearly
+// (align_corners=False) to gh x gw
+static void vit_pos_embed_host(const float *pe, int n, int C, int gh, int gw, float *out) {
+    for (int k = 0; k < C; ++k) out[k] = pe[k];
+    if (gh == n && gw == n) { memcpy(out + C, pe + C, (size_t)n * n * C * sizeof(float)); return; }
+    std::vector<float> plane((size_t)n * n), res((size_t)gh * gw);
+    for (int k = 0; k < C; ++k) {
+        for (int a = 0; a < n * n; ++a) plane[a] = pe[(size_t)(1 + a) * C + k];
+        bilinear_table(plane.data(), n, n, res.data(), gh, gw);
+        for (int a = 0; a < gh * gw; ++a) out[(size_t)(1 + a) * C + k] = res[a];
+    }
+}
+
 static void dinov2_pos_embed_host(const float *pe, int n, int C, int gh, int gw, float *out) {
     for (int k = 0; k < C; ++k) out[k] = pe[k];
     if (gh == n && gw == n) {
@@ -386,7 +404,8 @@ static int ensure_pos(dm_model *m, int gh, int gw) {
     if (m->pos_gh == gh && m->pos_gw == gw) return DM_OK;
     const int C = m->cfg.C;
     std::vector<float> out((size_t)(gh * gw + 1) * C);
-    dinov2_pos_embed_host(m->pos_embed_host.data(), m->pos_n, C, gh, gw, out.data());
+    if (m->cfg.family == 2) vit_pos_embed_host(m->pos_embed_host.data(), m->pos_n, C, gh, gw, out.data());
+    else dinov2_pos_embed_host(m->pos_embed_host.data(), m->pos_n, C, gh, gw, out.data());
     for (void *p : m->tab_owned) cudaFree(p);
     m->tab_owned.clear();
     DM_TRY(upload(m->tab_owned, out.data(), out.size() * 4, (void **)&m->pos_dev));
@@ -410,7 +429,7 @@ static int ensure_buffers(dm_model *m, int B, int nh, int nw) {
     DM_TRY(A("h", (size_t)B * N * C * h)); DM_TRY(A("qkv", (size_t)B * N * 3 * C * h)); DM_TRY(A("att", (size_t)B * N * C * h));
     DM_TRY(A("mlp", (size_t)B * N * 4 * C * h));
     for (int i = 0; i < 4; ++i) DM_TRY(A("feat" + std::to_string(i), (size_t)B * Np * C * h));
-    if (c.family == 1) DM_TRY(A("cat", (size_t)B * Np * 2 * C * h));
+    if (c.family != 0) DM_TRY(A("cat", (size_t)B * Np * 2 * C * h));
     const int sz[4][2] = {{gh * 4, gw * 4}, {gh * 2, gw * 2}, {gh, gw}, {(gh - 1) / 2 + 1, (gw - 1) / 2 + 1}};
     memcpy(b.sizes, sz, sizeof(sz));
     const int up[4][2] = {{sz[2][0], sz[2][1]}, {sz[1][0], sz[1][1]}, {sz[0][0], sz[0][1]}, {sz[0][0] * 2, sz[0][1] * 2}};
@@ -462,7 +481,7 @@ static int run_forward(dm_model *m, const uint8_t *rgb, int B, int H, int W, int
     auto W_ = [&](const std::string &k) { return m->w.at(k); };
     auto Bf = [&](const std::string &k) { return b.m.at(k); };
     const int C = c.C, heads = c.heads, Fp = m->Fp, P = c.patch, gh = nh / P, gw = nw / P, Np = gh * gw, N = Np + 1;
-    const bool beit = c.family == 1;
+    const bool beit = c.family == 1, midas = c.family != 0;
     const int cmap[3] = {2, 1, 0};   // the reference swaps R/B an odd number of times before the network sees the image (:381,550; dpt.py:213)
     DM_TRY(dm_preprocess_patchify(rgb, B, H, W, nh, nw, P, c.mean, c.stdv, cmap, Bf("patches"), m->kpad, st));
     m->launches += m->kpad > 3 * P * P ? 2 : 1;
@@ -485,7 +504,7 @@ static int run_forward(dm_model *m, const uint8_t *rgb, int B, int H, int W, int
         m->launches += 3 + (beit && gw % 16 == 0 ? 1 : 0);
         if (fi < 4 && i == c.layers[fi]) {
             const std::string f = "feat" + std::to_string(fi);
-            if (beit) {   // forward hook on the raw block output + ProjectReadout: GELU(Linear(cat(tokens, cls)))
+            if (midas) {  // forward hook on the raw block output + ProjectReadout: GELU(Linear(cat(tokens, cls)))
                 DM_TRY(dm_concat_readout_f16((float *)Bf("x"), B, N, C, Bf("cat"), st));
                 DM_TRY(gemm(m, Bf("cat"), 2 * C, W_("ro" + std::to_string(fi) + "_w"), 2 * C, B * Np, C, 2 * C, st, DM_EPI_STORE_F16, DM_ACT_GELU,
                             (float *)W_("ro" + std::to_string(fi) + "_b"), Bf(f), C));
@@ -555,7 +574,7 @@ DM_EXPORT int dm_model_create(dm_model_t **out, int model_type, const dm_weight_
     if (!out || !weights || !weights->items || weights->count <= 0) { set_error("dm_model_create: bad arguments"); return DM_E_INVALID; }
     *out = nullptr;
     ModelCfg cfg;
-    if (!model_cfg(model_type, cfg)) { set_error("dm_model_create: model_type %d has no native model (1, 2 = DPT-BEiT-L 512 / 384; 12, 13, 14 = Depth-Anything-V2 S / B / L)", model_type); return DM_E_UNSUPPORTED; }
+    if (!model_cfg(model_type, cfg)) { set_error("dm_model_create: model_type %d has no native model (1, 2 = DPT-BEiT-L 512 / 384; 3 = DPT-Large 384; 12, 13, 14 = Depth-Anything-V2 S / B / L)", model_type); return DM_E_UNSUPPORTED; }
     if (dtype != 0) { set_error("dm_model_create: only dtype 0 (fp16 operands, fp32 accumulation and residual stream) is implemented"); return DM_E_UNSUPPORTED; }
     DM_CUDA_CHECK(cudaSetDevice(device));
     dm_model *m = new dm_model();
@@ -582,6 +601,11 @@ DM_EXPORT int dm_model_destroy(dm_model_t *m) {
 DM_EXPORT int dm_dinov2_pos_embed(const float *pos_embed_host, int n, int C, int gh, int gw, float *out_host) {
     if (!pos_embed_host || !out_host || n <= 0 || C <= 0 || gh <= 0 || gw <= 0) { dm::set_error("dm_dinov2_pos_embed: bad arguments"); return DM_E_INVALID; }
     dm::dinov2_pos_embed_host(pos_embed_host, n, C, gh, gw, out_host);
+    return DM_OK;
+}
+DM_EXPORT int dm_vit_pos_embed(const float *pos_embed_host, int n, int C, int gh, int gw, float *out_host) {
+    if (!pos_embed_host || !out_host || n <= 0 || C <= 0 || gh <= 0 || gw <= 0) { dm::set_error("dm_vit_pos_embed: bad arguments"); return DM_E_INVALID; }
+    dm::vit_pos_embed_host(pos_embed_host, n, C, gh, gw, out_host);
     return DM_OK;
 }
 DM_EXPORT int dm_beit_rel_table(const float *table_host, int window, int heads, int gh, int gw, float *out_host) {
@@ -614,7 +638,7 @@ DM_EXPORT int dm_depth_forward(dm_model_t *m, const uint8_t *rgb, int B, int H, 
     if (!outer_capture) {
         DM_TRY(ensure_buffers(m, B, nh, nw));
         if (m->cfg.family == 1) DM_TRY(ensure_rel_tables(m, gh, gw)); else DM_TRY(ensure_pos(m, gh, gw));
-    } else if ((m->cfg.family == 1 && (m->tab_gh != gh || m->tab_gw != gw)) || (m->cfg.family == 0 && (m->pos_gh != gh || m->pos_gw != gw))) {
+    } else if ((m->cfg.family == 1 && (m->tab_gh != gh || m->tab_gw != gw)) || (m->cfg.family != 1 && (m->pos_gh != gh || m->pos_gw != gw))) {
         set_error("dm_depth_forward: resolution tables missing while capturing"); return DM_E_INVALID;
     }
     static int use_graph = -1;

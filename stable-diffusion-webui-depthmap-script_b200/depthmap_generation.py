@@ -7,7 +7,8 @@
 the bench.  The network forward is a sequence of C-ABI calls (tcgen05 GEMM / implicit-GEMM conv / fused attention /
 LayerNorm / resize kernels, include/depthmap_b200.h); PyTorch only owns device memory and the stream.
 
-Implemented model types: 1, 2 (MiDaS 3.1 DPT-BEiT-L 512 / 384) and 12, 13, 14 (Depth-Anything-V2 S/B/L).  Others raise NotImplementedError naming the type.
+Implemented model types: 1, 2 (MiDaS 3.1 DPT-BEiT-L 512 / 384), 3 (MiDaS 3.0 DPT-Large 384), 9 (ZoeDepth-NK) and 12, 13, 14
+(Depth-Anything-V2 S/B/L).  Others raise NotImplementedError naming the type.
 Weights: a state_dict in the upstream checkpoint layout (``depth_anything_v2_vit{s,b,l}.pth``), packed once at load
 into the kernels' layout (fp16 GEMM operands, (ky,kx,cin)-ordered conv filters, ConvTranspose as GEMM + pixel shuffle).
 """
@@ -627,6 +628,54 @@ class DptBeitEngine(DepthAnythingV2Engine):
         self.ops.gemm(b['cat'], 2 * C, rw, 2 * C, B * (N - 1), C, 2 * C, act=_lib.ACT_GELU, bias=rb, C=b['feat'][fi], ldc=C)
 
 
+class DptVitEngine(DptBeitEngine):
+    """MiDaS 3.0 dpt_large_384 (model type 3) on the sm_100a kernels, op-level path: timm's vit_large_patch16_384 driven by
+    the reference's forward_flex (dmidas/backbones/vit.py:12-79,107-118) — absolute position embedding resized bilinearly to
+    the current grid, plain (un-biased) attention, no LayerScale — with the hooks, ProjectReadout, reassemble stage and DPT
+    decoder it shares with the BEiT models (dmidas/dpt_depth.py:31-166)."""
+
+    CONFIGS = {
+        'vitl16_384': dict(embed_dim=1024, depth=24, heads=16, features=256, out_channels=[256, 512, 1024, 1024], layers=[5, 11, 17, 23], window=24),
+        'vit_tiny': dict(embed_dim=128, depth=4, heads=2, features=64, out_channels=[64, 64, 128, 128], layers=[0, 1, 2, 3], window=4),
+    }
+
+    def _pack(self, sd):
+        import torch
+        C = self.cfg['embed_dim']
+        p = 'pretrained.model.'
+        m = dict(sd)
+        for i in range(self.cfg['depth']):      # present the ViT block in the layout the BEiT packer reads
+            b = p + f'blocks.{i}.'
+            qb = sd[b + 'attn.qkv.bias'].float()
+            m[b + 'attn.q_bias'], m[b + 'attn.v_bias'] = qb[:C], qb[2 * C:]
+            m[b + 'gamma_1'] = torch.ones(C)
+            m[b + 'gamma_2'] = torch.ones(C)
+            m[b + 'attn.relative_position_bias_table'] = torch.zeros(1, self.cfg['heads'])
+        super()._pack(m)
+        # the key projection DOES have a bias here: restore the full qkv bias the BEiT packer zeroed
+        for i, blk in enumerate(self.w['blocks']):
+            blk['qkv_b'] = sd[p + f'blocks.{i}.attn.qkv.bias'].detach().to(self.device, torch.float32).contiguous()
+        self._pos_embed = sd[p + 'pos_embed'].detach().to(self.device, torch.float32).contiguous()
+
+    def _pos(self, gh, gw):
+        """_resize_pos_embed (vit.py:16-31) through the host routine the model-level C-ABI uses (bit-identical tables)."""
+        import torch
+        key = (gh, gw)
+        if key not in self._pos_cache:
+            pe = self._pos_embed
+            C = pe.shape[-1]
+            N = pe.shape[1] - 1
+            n = int(round(math.sqrt(N)))
+            src = np.ascontiguousarray(pe.reshape(N + 1, C).cpu().numpy(), dtype=np.float32)
+            dst = np.empty((gh * gw + 1, C), dtype=np.float32)
+            _lib.check(self.ops.L.dm_vit_pos_embed(src.ctypes.data, n, C, gh, gw, dst.ctypes.data), "dm_vit_pos_embed")
+            self._pos_cache[key] = torch.from_numpy(dst).to(self.device)
+        return self._pos_cache[key]
+
+    def attention(self, i, b, B, N, heads, C, gh, gw):
+        self.ops.attention(b['qkv'], B, N, heads, (C // heads) ** -0.5, b['att'])
+
+
 class NativeDepthModel:
     """Thin caller of the model-level C-ABI (include/depthmap_b200.h: dm_model_create / dm_depth_forward / dm_model_destroy,
     csrc/model.cu): the handle owns the packed weights, the activation buffers, the resolution tables and a captured CUDA
@@ -1011,6 +1060,17 @@ class ModelHolder:
                 if "optimizer" in sd:       # dmidas/base_model.py:13: training checkpoints wrap the weights
                     sd = sd["model"]
             model = NativeDepthModel(sd, model_type, torch.device(device))
+        elif model_type == 3:  # dpt_large_384 (MiDaS 3.0)
+            if self.weights_provider is not None:
+                sd = self.weights_provider(model_type)
+            else:
+                model_path = "./models/midas/dpt_large-midas-2f21e586.pt"
+                if not os.path.exists(model_path):
+                    raise FileNotFoundError(f"{model_path} not found (depthmap_b200 does not download checkpoints)")
+                sd = torch.load(model_path, map_location='cpu')
+                if "optimizer" in sd:
+                    sd = sd["model"]
+            model = NativeDepthModel(sd, model_type, torch.device(device))
         elif model_type == 9:  # zoedepth_nk (src/depthmap_generation.py:221-226: ZoeD_M12_NK.pt)
             if self.weights_provider is not None:
                 sd = self.weights_provider(model_type)
@@ -1024,7 +1084,7 @@ class ModelHolder:
             model = ZoeDepthNKEngine(sd, torch.device(device))
         else:
             raise NotImplementedError(f"model_type {model_type} is not implemented in depthmap_b200 yet "
-                                      f"(implemented: 1, 2 = DPT-BEiT-L 512/384; 9 = ZoeDepth-NK; 12, 13, 14 = Depth-Anything-V2 S/B/L)")
+                                      f"(implemented: 1, 2 = DPT-BEiT-L 512/384; 3 = DPT-Large 384; 9 = ZoeDepth-NK; 12, 13, 14 = Depth-Anything-V2 S/B/L)")
         self.depth_model = model
         self.depth_model_type = model_type
         self.resize_mode = "minimal"
@@ -1074,7 +1134,7 @@ class ModelHolder:
         """uint8 CUDA [B,H,W,3] -> (float32 CUDA [B,H,W], invert flag).  Batched form of get_raw_prediction."""
         if self.depth_model is None:
             raise RuntimeError("no depth model loaded; call ensure_models first")
-        if self.depth_model_type in (1, 2, 9, 12, 13, 14):
+        if self.depth_model_type in (1, 2, 3, 9, 12, 13, 14):
             pred = self.depth_model.forward_batch(rgb, net_width, net_height)
         else:
             raise NotImplementedError(f"model_type {self.depth_model_type}")

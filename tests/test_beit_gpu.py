@@ -45,3 +45,29 @@ def test_modelholder_beit(cuda_device):
     assert ModelHolder.get_default_net_size(1) == [512, 512] and ModelHolder.get_default_net_size(2) == [384, 384]
     with pytest.raises((FileNotFoundError, NotImplementedError)):
         mh.ensure_models(1, cuda_device, False)
+
+
+# ---- MiDaS 3.0 dpt_large_384 (model type 3): ViT-L/16 trunk, same decoder ---------------------------------------------------
+def _check_vit(cuda_device, name, hw, net, B):
+    import torch
+    from depthmap_b200.depthmap_generation import DptVitEngine
+    from oracle import beit_dpt, synth_weights
+    from synth import synth_rgb
+    sd = synth_weights.make_beit_dpt_state_dict(name, seed=5)
+    eng = DptVitEngine(sd, name, cuda_device)
+    imgs = [synth_rgb(hw[0], hw[1], 30 + s) for s in range(B)]
+    got = eng.forward_batch(torch.from_numpy(np.stack(imgs)).to(cuda_device), net[0], net[1]).cpu().numpy()
+    for i, img in enumerate(imgs):
+        want, inv = beit_dpt.get_raw_prediction(img, sd, name, net[0], net[1])
+        assert float(want.max() - want.min()) > 0.05 and inv is False
+        ref16 = precision.reference_fp16_error('beit', img, sd, name, net, want, cuda_device)
+        precision.check(f"{name} {hw} net {net} img{i}", got[i], want, ref16)
+
+
+@pytest.mark.parametrize("hw,net", [((64, 64), (64, 64)), ((96, 128), (96, 96)), ((70, 50), (64, 64))])
+def test_vit_tiny_vs_oracle(cuda_device, hw, net):
+    _check_vit(cuda_device, 'vit_tiny', hw, net, 2)
+
+
+def test_dpt_large_384_vs_oracle(cuda_device):
+    _check_vit(cuda_device, 'vitl16_384', (384, 480), (384, 384), 1)

@@ -84,3 +84,48 @@ def test_relative_position_index_equals_hf():
         want = hf.generate_relative_position_index(win)
         got = beit_dpt.gen_relative_position_index(win)
         assert torch.equal(want, got), win
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dpt_large_384 (model type 3): the ViT-L/16 trunk of the oracle against HuggingFace's ViTModel at the native resolution
+# (the reference resizes the position grid bilinearly, HF bicubically, so only the native grid is comparable)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_vit_trunk_equals_hf_vit():
+    from transformers import ViTConfig, ViTModel
+    from oracle import beit_dpt, synth_weights
+    cfg = beit_dpt.CONFIGS['vit_tiny']
+    sd = synth_weights.make_beit_dpt_state_dict('vit_tiny', seed=6)
+    C, depth, heads, win = cfg['embed_dim'], cfg['depth'], cfg['heads'], cfg['window']
+    hc = ViTConfig(hidden_size=C, num_hidden_layers=depth, num_attention_heads=heads, intermediate_size=4 * C, image_size=16 * win,
+                   patch_size=16, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-6, hidden_act="gelu", qkv_bias=True)
+    m = ViTModel(hc, add_pooling_layer=False).eval()
+    p = 'pretrained.model.'
+    new = {'embeddings.cls_token': sd[p + 'cls_token'], 'embeddings.position_embeddings': sd[p + 'pos_embed'],
+           'embeddings.patch_embeddings.projection.weight': sd[p + 'patch_embed.proj.weight'],
+           'embeddings.patch_embeddings.projection.bias': sd[p + 'patch_embed.proj.bias'],
+           'layernorm.weight': sd[p + 'norm.weight'], 'layernorm.bias': sd[p + 'norm.bias']}
+    for i in range(depth):
+        b, h = p + f'blocks.{i}.', f'encoder.layer.{i}.'
+        qw, qb = sd[b + 'attn.qkv.weight'], sd[b + 'attn.qkv.bias']
+        for k, nm in enumerate(('query', 'key', 'value')):
+            new[h + f'attention.attention.{nm}.weight'] = qw[k * C:(k + 1) * C]
+            new[h + f'attention.attention.{nm}.bias'] = qb[k * C:(k + 1) * C]
+        new[h + 'attention.output.dense.weight'] = sd[b + 'attn.proj.weight']
+        new[h + 'attention.output.dense.bias'] = sd[b + 'attn.proj.bias']
+        new[h + 'intermediate.dense.weight'] = sd[b + 'mlp.fc1.weight']
+        new[h + 'intermediate.dense.bias'] = sd[b + 'mlp.fc1.bias']
+        new[h + 'output.dense.weight'] = sd[b + 'mlp.fc2.weight']
+        new[h + 'output.dense.bias'] = sd[b + 'mlp.fc2.bias']
+        new[h + 'layernorm_before.weight'] = sd[b + 'norm1.weight']
+        new[h + 'layernorm_before.bias'] = sd[b + 'norm1.bias']
+        new[h + 'layernorm_after.weight'] = sd[b + 'norm2.weight']
+        new[h + 'layernorm_after.bias'] = sd[b + 'norm2.bias']
+    res = m.load_state_dict({k: v.float() for k, v in new.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        want = m(pixel_values=x, output_hidden_states=True).hidden_states
+        got = beit_dpt.vit_backbone_hooks(sd, x, cfg)
+    for i, g in enumerate(got):
+        err = float((g - want[i + 1]).abs().max()) / float(want[i + 1].abs().max())
+        assert err < 2e-5, (i, err)

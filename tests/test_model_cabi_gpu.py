@@ -56,6 +56,23 @@ def test_native_beit_equals_op_level_path(cuda_device, hw, net):
     nat.close()
 
 
+@pytest.mark.parametrize("hw,net", [((64, 64), (64, 64)), ((96, 128), (96, 96))])
+def test_native_vit_equals_op_level_path(cuda_device, hw, net):
+    """dpt_large_384 family (model type 3; -101 = its structural test configuration)"""
+    import torch
+    from depthmap_b200.depthmap_generation import DptVitEngine, NativeDepthModel
+    from oracle import synth_weights
+    sd = synth_weights.make_beit_dpt_state_dict('vit_tiny', seed=5)
+    eng = DptVitEngine(sd, 'vit_tiny', cuda_device)
+    nat = NativeDepthModel(sd, -101, cuda_device)
+    rgb = torch.from_numpy(_imgs(2, *hw, seed=11)).to(cuda_device)
+    want = eng.forward_batch(rgb, net[0], net[1]).cpu().numpy()
+    for call in range(3):
+        got = nat.forward_batch(rgb, net[0], net[1]).cpu().numpy()
+        assert np.array_equal(got, want), (call, float(np.abs(got - want).max()))
+    nat.close()
+
+
 def test_native_beit512_bit_exact_and_outer_graph(cuda_device):
     """dpt_beit_large_512 at its native window (no table resize): the native model reproduces the op-level path exactly, also
     when its launches are recorded into a caller's CUDA graph."""
