@@ -260,6 +260,20 @@ long long dm_model_launches(const dm_model_t *model);
 int dm_depth_forward(dm_model_t *model, const uint8_t *rgb, int B, int H, int W, int net_w, int net_h, float *depth_out, int out_h, int out_w,
                      void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * D8 — LeReS (ResNeXt-101 32x8d + FTB / FFM / AO decoder), csrc/leres_kernels.cu: the non-GEMM pieces.   replaces parts of
+ *   estimateleres / scale_torch (src/depthmap_generation.py:406-440), lib/Resnext_torch.py:196-220, lib/network_auxi.py:95-215.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* uint8 RGB [B,H,W,3] -> /255 -> cv2.resize(bilinear) to net_h x net_w -> (x - mean) / std -> im2col of the 7x7 stride-2 pad-3
+ * stem convolution: fp16 [B*Ho*Wo, 192], taps ordered (ky, kx, c), columns 147..191 zero */
+int dm_leres_stem_im2col(const uint8_t *rgb, int B, int H, int W, int net_h, int net_w, const float *mean_host, const float *std_host, void *out,
+                         void *stream);
+int dm_maxpool3x3s2_nhwc_f16(const void *in, int B, int H, int W, int C, void *out, void *stream);   /* kernel 3, stride 2, padding 1 */
+int dm_subsample2_nhwc_f16(const void *in, int B, int H, int W, int C, void *out, void *stream);     /* x[:, ::2, ::2, :] */
+int dm_add_f16(const void *a, const void *b, void *out, long long n, void *stream);
+/* dm_resize_f32 reading pixel (y, x) at in[(y * Win + x) * ld] (channel 0 of an [pixels, ld] fp32 GEMM output) */
+int dm_resize_f32_ld(const float *in, int ld, int B, int Hin, int Win, float *out, int Hout, int Wout, int mode, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

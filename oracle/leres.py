@@ -88,11 +88,12 @@ def forward(sd, x):
     return decoder(encoder(x, sd), sd)
 
 
-def preprocess(rgb_uint8, w, h):
-    """estimateleres + scale_torch: channel flip, cv2.resize (bilinear) to (w, h), float32 ToTensor WITHOUT the /255 (the
-    array is float32 already, so torchvision only transposes it), ImageNet mean / std on the 0..255-scaled values."""
+def preprocess(img, w, h):
+    """estimateleres + scale_torch (src/depthmap_generation.py:406-440) on the image estimateleres receives: channel flip,
+    cv2.resize (bilinear, in the array's own dtype) to (w, h), float32, ToTensor WITHOUT a /255 (torchvision only transposes float
+    arrays), ImageNet mean / std."""
     import cv2
-    img = np.asarray(rgb_uint8)
+    img = np.asarray(img)
     a = cv2.resize(img[:, :, ::-1].copy(), (w, h))
     t = torch.from_numpy(a.astype(np.float32).transpose(2, 0, 1).copy())
     mean = torch.tensor((0.485, 0.456, 0.406)).view(3, 1, 1)
@@ -101,10 +102,19 @@ def preprocess(rgb_uint8, w, h):
 
 
 @torch.no_grad()
-def get_raw_prediction(rgb_uint8, sd, w=448, h=448):
-    """ModelHolder.get_raw_prediction for model type 0 (res101): (float32 [H,W], invert=True)."""
+def estimateleres(img, sd, w=448, h=448):
+    """The reference function itself (:406-421) for whatever image array it is handed."""
     import cv2
-    img = np.asarray(rgb_uint8)
+    img = np.asarray(img)
     pred = forward(sd, preprocess(img, w, h)).squeeze().cpu().numpy()
-    pred = cv2.resize(pred, (img.shape[1], img.shape[0]), interpolation=cv2.INTER_CUBIC)
-    return pred, True
+    return cv2.resize(pred, (img.shape[1], img.shape[0]), interpolation=cv2.INTER_CUBIC)
+
+
+@torch.no_grad()
+def get_raw_prediction(rgb_uint8, sd, w=448, h=448):
+    """ModelHolder.get_raw_prediction for model type 0 (res101): (float32 [H,W], invert=True).  The holder hands estimateleres
+    `cv2.cvtColor(image, COLOR_BGR2RGB) / 255.0` (:381), i.e. a float64 image in [0, 1] with swapped channels, which
+    estimateleres swaps back."""
+    import cv2
+    img = cv2.cvtColor(np.asarray(rgb_uint8), cv2.COLOR_BGR2RGB) / 255.0
+    return estimateleres(img, sd, w, h), True

@@ -199,3 +199,58 @@ def make_zoedepth_head_state_dict(feat_ch=256, out_conv_ch=32, seed=0, dtype=tor
         conv(f"projectors.{i}._net.0", emb // 2, feat_ch)
         conv(f"projectors.{i}._net.2", emb, emb // 2)
     return sd
+
+
+def make_leres_state_dict(seed=0, dtype=torch.float32):
+    """Seeded synthetic state_dict with the keys and shapes of the reference's RelDepthModel('resnext101').state_dict()
+    (lib/multi_depth_model_woauxi.py, lib/Resnext_torch.py, lib/network_auxi.py; `num_batches_tracked` buffers left out):
+    ResNeXt-101 32x8d encoder + FTB / FFM / AO decoder.  Fan-in scaled filters, BatchNorm statistics near identity, bn3 scaled
+    down so 33 residual blocks keep activations O(1) (the recipe tests/test_oracle_pin.py uses for the reference module)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(key, co, ci, k, bias=False):
+        sd[key + '.weight'] = (torch.randn(co, ci, k, k, generator=g) * (1.0 / (ci * k * k) ** 0.5)).to(dtype)
+        if bias:
+            sd[key + '.bias'] = (0.05 * torch.randn(co, generator=g)).to(dtype)
+
+    def bn(key, c, gain=1.0):
+        sd[key + '.weight'] = (gain + 0.05 * torch.randn(c, generator=g)).to(dtype)
+        sd[key + '.bias'] = (0.05 * torch.randn(c, generator=g)).to(dtype)
+        sd[key + '.running_mean'] = (0.1 * torch.randn(c, generator=g)).to(dtype)
+        sd[key + '.running_var'] = (0.5 + torch.rand(c, generator=g)).to(dtype)
+
+    E = 'depth_model.encoder_modules.encoder.'
+    conv(E + 'conv1', 64, 3, 7)
+    bn(E + 'bn1', 64)
+    inplanes = 64
+    for li, (planes, nb) in enumerate(zip((64, 128, 256, 512), (3, 4, 23, 3)), start=1):
+        width = planes * 8 // 64 * 32
+        for bi in range(nb):
+            p = f'{E}layer{li}.{bi}'
+            conv(p + '.conv1', width, inplanes, 1)
+            bn(p + '.bn1', width)
+            conv(p + '.conv2', width, width // 32, 3)
+            bn(p + '.bn2', width)
+            conv(p + '.conv3', planes * 4, width, 1)
+            bn(p + '.bn3', planes * 4, gain=0.3)
+            if bi == 0:
+                conv(p + '.downsample.0', planes * 4, inplanes, 1)
+                bn(p + '.downsample.1', planes * 4)
+            inplanes = planes * 4
+    D = 'depth_model.decoder_modules.'
+
+    def ftb(p, ci, cm):
+        conv(p + '.conv1', cm, ci, 3, bias=True)
+        conv(p + '.conv_branch.1', cm, cm, 3, bias=True)
+        bn(p + '.conv_branch.2', cm)
+        conv(p + '.conv_branch.4', cm, cm, 3, bias=True)
+    ftb(D + 'conv', 2048, 512)
+    conv(D + 'conv1', 256, 512, 3, bias=True)
+    for k, ci in (('ffm2', 1024), ('ffm1', 512), ('ffm0', 256)):
+        ftb(D + k + '.ftb1', ci, 256)
+        ftb(D + k + '.ftb2', 256, 256)
+    conv(D + 'outconv.adapt_conv.0', 128, 256, 3, bias=True)
+    bn(D + 'outconv.adapt_conv.1', 128)
+    conv(D + 'outconv.adapt_conv.3', 1, 128, 3, bias=True)
+    return sd

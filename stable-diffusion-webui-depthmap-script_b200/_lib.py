@@ -77,6 +77,7 @@ EXPORTS = [
     "dm_video_workspace_bytes", "dm_video_blend", "dm_video_minmax", "dm_video_scale_f32", "dm_video_select_init", "dm_video_select_hist",
     "dm_video_select_pick", "dm_video_select_bounds", "dm_video_scale_f64",
     "dm_model_create", "dm_model_destroy", "dm_model_net_size", "dm_model_launches", "dm_depth_forward", "dm_dinov2_pos_embed", "dm_beit_rel_table", "dm_vit_pos_embed",
+    "dm_leres_stem_im2col", "dm_maxpool3x3s2_nhwc_f16", "dm_subsample2_nhwc_f16", "dm_add_f16", "dm_resize_f32_ld",
 ]
 
 
@@ -154,6 +155,12 @@ def _bind_optional(L):
         L.dm_resize_f32.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp]
         L.dm_im2col_s2_f16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
         L.dm_concat_readout_f16.argtypes = [vp, i32, i32, i32, vp, vp]
+    if hasattr(L, "dm_leres_stem_im2col"):
+        L.dm_leres_stem_im2col.argtypes = [vp, i32, i32, i32, i32, i32, c.POINTER(c.c_float), c.POINTER(c.c_float), vp, vp]
+        L.dm_maxpool3x3s2_nhwc_f16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+        L.dm_subsample2_nhwc_f16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+        L.dm_add_f16.argtypes = [vp, vp, vp, c.c_longlong, vp]
+        L.dm_resize_f32_ld.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     if hasattr(L, "dm_zoe_clb_final"):
         L.dm_zoe_preprocess_patchify.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
         L.dm_layernorm_post_f16.argtypes = [vp, c.c_longlong, i32, vp, vp, f32, vp, vp]

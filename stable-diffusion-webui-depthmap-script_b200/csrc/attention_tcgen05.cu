@@ -80,6 +80,7 @@ struct Attn2Params {
     const float *rel_table;   // [H, nrd] * log2(e)   (modes 2, 3)
     const float *rel_rowmax;  // [H, N]: max_k bias(q, k) * log2(e)   (modes 2, 3) — lets the first-tile max pass skip the bias gather
     int nrd, gh, gw;
+    int phase_token;          // fwd4: alternate the two query tiles' exponentiation phases (see attention_fwd4_kernel)
 };
 
 constexpr int A2_THREADS = 64 + 256;
@@ -763,6 +764,13 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
             rp_e0 = pp.nrd - 1 - rp_base;
         }
         const uint64_t scale2 = pack2(p.scale_log2e, p.scale_log2e);
+        // The exponentiation phase of a tile keeps the MUFU pipe (16 lanes / SM) busy for ~1000 cycles per SM sub-partition and
+        // issues little else; the score phase (bias, scale, max) is FMA / LDS work.  Left alone, both query tiles drift into the
+        // same phase (they start together and wait on the same tensor pipe), the MUFU pipe saturates for half the time and
+        // idles for the other half.  A token handed back and forth through two named barriers makes the tiles alternate:
+        // tile A exponentiates while tile B prepares its scores, and vice versa.
+        const bool token = pp.phase_token && b_active;
+        if (token && g == 1) asm volatile("bar.arrive 9, 512;" ::: "memory");       // tile A goes first
         int xch_n = 0;
         auto pair_max = [&](float v) {
             float *slot = s_xch + (((xch_n & 1) * 2 + g) * 128 + row) * 2;
@@ -898,6 +906,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                 }
             }
             // ---- p = 2^u -> fp16 -> swizzled K-major P tile --------------------------------------------------------------
+            if (token) { if (g == 0) asm volatile("bar.sync 9, 512;" ::: "memory"); else asm volatile("bar.sync 10, 512;" ::: "memory"); }
             auto emit = [&](int c) {
                 uint32_t packed[8];
 #pragma unroll
@@ -916,6 +925,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                 for (int c = 0; c < 4; ++c)
                     if (c * 16 < nmine) emit(c);
             }
+            if (token) { if (g == 0) asm volatile("bar.arrive 10, 512;" ::: "memory"); else if (j + 1 < num_kv) asm volatile("bar.arrive 9, 512;" ::: "memory"); }
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
@@ -997,6 +1007,7 @@ int attention_f16(const __half *qkv, const AttnParams &p, cudaStream_t stream, c
     }
     Attn2Params pp;
     pp.a = p; pp.rel_table = rel_table; pp.rel_rowmax = rel_rowmax; pp.nrd = nrd; pp.gh = gh; pp.gw = gw;
+    { const char *e = getenv("DEPTHMAP_B200_ATTN_TOKEN"); pp.phase_token = (e && e[0] == '0') ? 0 : 1; }
     if (rel_table) {
         if (gh * gw + 1 != p.N || nrd != (2 * gh - 1) * (2 * gw - 1) + 3) { set_error("attention_f16: relative-position mode needs N = gh*gw+1 and nrd = (2gh-1)(2gw-1)+3"); return DM_E_INVALID; }
         const char *e = getenv("DEPTHMAP_B200_ATTN_GENERIC");   // read per call: the tests flip it to cover both table modes

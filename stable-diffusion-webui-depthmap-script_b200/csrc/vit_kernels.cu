@@ -204,15 +204,16 @@ __global__ void __launch_bounds__(256) resize_bilinear_nhwc_kernel(const __half 
 }
 
 // single-channel fp32 resize: mode 0 = bilinear align_corners=True, mode 1 = bicubic align_corners=False (A = -0.75)
+// `ld` = distance between consecutive input pixels in floats (1 for a dense map; N for channel 0 of an [pixels, N] GEMM output)
 __global__ void __launch_bounds__(256) resize_f32_kernel(const float *__restrict__ in, int B, int Hin, int Win, float *__restrict__ out,
-                                                         int Hout, int Wout, int mode) {
+                                                         int Hout, int Wout, int mode, int ld) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Hout * Wout;
     if (idx >= total) return;
     const int x = (int)(idx % Wout);
     const int y = (int)((idx / Wout) % Hout);
     const int b = (int)(idx / ((long long)Wout * Hout));
-    const float *img = in + (long long)b * Hin * Win;
+    const float *img = in + (long long)b * Hin * Win * ld;
     if (mode == 0) {
         const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
         const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
@@ -220,8 +221,8 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float *__restrict
         const int y0 = min((int)fy, Hin - 1), x0 = min((int)fx, Win - 1);
         const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
         const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-        out[idx] = hy * (hx * img[(long long)y0 * Win + x0] + lx * img[(long long)y0 * Win + x1]) +
-                   ly * (hx * img[(long long)y1 * Win + x0] + lx * img[(long long)y1 * Win + x1]);
+        out[idx] = hy * (hx * img[((long long)y0 * Win + x0) * ld] + lx * img[((long long)y0 * Win + x1) * ld]) +
+                   ly * (hx * img[((long long)y1 * Win + x0) * ld] + lx * img[((long long)y1 * Win + x1) * ld]);
     } else {
         const float sy = (float)Hin / (float)Hout, sx = (float)Win / (float)Wout;
         float fy = sy * ((float)y + 0.5f) - 0.5f, fx = sx * ((float)x + 0.5f) - 0.5f;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float *__restrict
             const int yy = min(max(iy - 1 + j, 0), Hin - 1);
             float r = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) r += cx[i] * img[(long long)yy * Win + min(max(ix - 1 + i, 0), Win - 1)];
+            for (int i = 0; i < 4; ++i) r += cx[i] * img[((long long)yy * Win + min(max(ix - 1 + i, 0), Win - 1)) * ld];
             acc += cy[j] * r;
         }
         out[idx] = acc;
@@ -348,7 +349,16 @@ DM_EXPORT int dm_resize_bilinear_nhwc_f16(const void *in, int B, int Hin, int Wi
 DM_EXPORT int dm_resize_f32(const float *in, int B, int Hin, int Win, float *out, int Hout, int Wout, int mode, void *stream_) {
     using namespace dm;
     const long long total = (long long)B * Hout * Wout;
-    resize_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(in, B, Hin, Win, out, Hout, Wout, mode);
+    resize_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(in, B, Hin, Win, out, Hout, Wout, mode, 1);
+    DM_LAUNCH_CHECK("resize_f32_kernel");
+    return DM_OK;
+}
+
+DM_EXPORT int dm_resize_f32_ld(const float *in, int ld, int B, int Hin, int Win, float *out, int Hout, int Wout, int mode, void *stream_) {
+    using namespace dm;
+    if (ld < 1) { set_error("dm_resize_f32_ld: bad pixel stride"); return DM_E_INVALID; }
+    const long long total = (long long)B * Hout * Wout;
+    resize_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(in, B, Hin, Win, out, Hout, Wout, mode, ld);
     DM_LAUNCH_CHECK("resize_f32_kernel");
     return DM_OK;
 }

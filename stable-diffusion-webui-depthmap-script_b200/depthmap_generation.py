@@ -86,7 +86,7 @@ class _Ops:
         self.launches += 1
 
     def conv3x3(self, act_t, B, H, W_, Cin, Wt, Cout, epi=_lib.EPI_STORE_F16, act=_lib.ACT_NONE, bias=None, C=None, C2=None,
-                R=None, R2=None, X=None, gamma=None, head_b2=0.0):
+                R=None, R2=None, X=None, gamma=None, head_b2=0.0, ldx=1):
         d = _lib.GemmDesc()
         d.N, d.epi, d.act = Cout, epi, act
         d.bias = bias.data_ptr() if bias is not None else None
@@ -98,7 +98,7 @@ class _Ops:
         d.R2 = R2.data_ptr() if R2 is not None else None
         d.ldr2 = Cout
         d.X = X.data_ptr() if X is not None else None
-        d.ldx = 1
+        d.ldx = ldx
         d.gamma = gamma.data_ptr() if gamma is not None else None
         d.head_b2 = head_b2
         _lib.check(self.L.dm_conv3x3_ex(act_t.data_ptr(), B, H, W_, Cin, Wt.data_ptr(), ctypes.byref(d), _lib.stream_ptr()), "dm_conv3x3_ex")
@@ -676,6 +676,219 @@ class DptVitEngine(DptBeitEngine):
         self.ops.attention(b['qkv'], B, N, heads, (C // heads) ** -0.5, b['att'])
 
 
+class LeresEngine:
+    """LeReS / res101 (model type 0) on the sm_100a kernels: estimateleres (src/depthmap_generation.py:406-440) around
+    RelDepthModel('resnext101') (lib/multi_depth_model_woauxi.py:6-32, lib/Resnext_torch.py:60-220, lib/network_auxi.py:15-215).
+    NHWC fp16 activations, fp32 accumulation.  1x1 convolutions are GEMMs, 3x3 ones the implicit-GEMM conv; the 32-group 3x3
+    convolutions use block-diagonal dense filters (exact: the extra products are zeros), the three stride-2 ones go through the
+    strided im2col; BatchNorm (running statistics, eps 1e-5) is folded into filters and biases when the checkpoint is packed; the
+    bottleneck's `relu(out + identity)` and FTB's `relu(x + branch)` come out of the GEMM epilogue's relu copy (C2)."""
+
+    LAYERS = (3, 4, 23, 3)
+    GROUPS = 32
+    ENC = "depth_model.encoder_modules.encoder."
+    DEC = "depth_model.decoder_modules."
+    MEAN = (0.485, 0.456, 0.406)
+    STD = (0.229, 0.224, 0.225)
+
+    def __init__(self, state_dict, device):
+        self.device = device
+        self.ops = _Ops()
+        self._bufs, self._buf_key = {}, None
+        self._pack(state_dict)
+
+    # ---- weights -------------------------------------------------------------------------------------------------------
+    def _fold(self, sd, conv, bn):
+        """conv weight [Co, Ci/g, kh, kw] (+ optional bias) followed by BatchNorm (inference) -> (weight, bias) in fp32"""
+        import torch
+        w = sd[conv + '.weight'].detach().float()
+        b = sd[conv + '.bias'].detach().float() if conv + '.bias' in sd else torch.zeros(w.shape[0])
+        if bn is not None:
+            scale = sd[bn + '.weight'].detach().float() / torch.sqrt(sd[bn + '.running_var'].detach().float() + 1e-5)
+            w = w * scale.view(-1, 1, 1, 1)
+            b = (b - sd[bn + '.running_mean'].detach().float()) * scale + sd[bn + '.bias'].detach().float()
+        return w, b
+
+    def _mat(self, w, b, kpad=None, npad=None):
+        import torch
+        co = w.shape[0]
+        m = w.reshape(co, -1)
+        k, n = kpad or m.shape[1], npad or co
+        t = torch.zeros(n, k, dtype=torch.float16)
+        t[:co, :m.shape[1]] = m.to(torch.float16)
+        bb = torch.zeros(n, dtype=torch.float32)
+        bb[:co] = b
+        return t.to(self.device).contiguous(), bb.to(self.device).contiguous()
+
+    def _conv3(self, w, b, groups=1, npad=None):
+        """[Co, Ci/g, 3, 3] -> dense fp16 [Co(pad), 9 * Ci], K ordered (ky, kx, ci); groups become diagonal blocks"""
+        import torch
+        co, cig = w.shape[:2]
+        ci = cig * groups
+        n = npad or co
+        t = torch.zeros(n, 3, 3, ci, dtype=torch.float16)
+        wp = w.permute(0, 2, 3, 1).to(torch.float16)             # [Co, ky, kx, Ci/g]
+        cog = co // groups
+        for g in range(groups):
+            t[g * cog:(g + 1) * cog, :, :, g * cig:(g + 1) * cig] = wp[g * cog:(g + 1) * cog]
+        bb = torch.zeros(n, dtype=torch.float32)
+        bb[:co] = b
+        return t.reshape(n, 9 * ci).to(self.device).contiguous(), bb.to(self.device).contiguous()
+
+    def _pack(self, sd):
+        import torch
+        E, D = self.ENC, self.DEC
+        w = {}
+        sw, sb = self._fold(sd, E + 'conv1', E + 'bn1')            # [64, 3, 7, 7] -> [64, (ky, kx, c)] padded to 192
+        w['stem'] = self._mat(sw.permute(0, 2, 3, 1).contiguous(), sb, kpad=192)
+        blocks = []
+        for li, nb in enumerate(self.LAYERS, start=1):
+            for bi in range(nb):
+                p = f"{E}layer{li}.{bi}"
+                blk = dict(stride=2 if (bi == 0 and li > 1) else 1)
+                blk['c1'] = self._mat(*self._fold(sd, p + '.conv1', p + '.bn1'))
+                blk['c2'] = self._conv3(*self._fold(sd, p + '.conv2', p + '.bn2'), groups=self.GROUPS)
+                blk['c3'] = self._mat(*self._fold(sd, p + '.conv3', p + '.bn3'))
+                blk['down'] = self._mat(*self._fold(sd, p + '.downsample.0', p + '.downsample.1')) if bi == 0 else None
+                blk['width'], blk['cout'] = blk['c1'][0].shape[0], blk['c3'][0].shape[0]
+                blocks.append(blk)
+        w['blocks'] = blocks
+
+        def ftb(p):
+            return dict(c1=self._conv3(*self._fold(sd, p + '.conv1', None)),
+                        b1=self._conv3(*self._fold(sd, p + '.conv_branch.1', p + '.conv_branch.2')),
+                        b4=self._conv3(*self._fold(sd, p + '.conv_branch.4', None)))
+        w['conv'] = ftb(D + 'conv')
+        w['conv1'] = self._conv3(*self._fold(sd, D + 'conv1', None))
+        for k in ('ffm2', 'ffm1', 'ffm0'):
+            w[k] = (ftb(D + k + '.ftb1'), ftb(D + k + '.ftb2'))
+        a = D + 'outconv.adapt_conv'
+        w['ao0'] = self._conv3(*self._fold(sd, a + '.0', a + '.1'))
+        w['ao3'] = self._conv3(*self._fold(sd, a + '.3', None), npad=32)
+        self.w = w
+
+    # ---- buffers: a simple keyed pool (every tensor of a forward has its own name) ---------------------------------
+    def _buf(self, name, shape, dtype=None):
+        import torch
+        dtype = dtype or torch.float16
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(*shape, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    # ---- forward ---------------------------------------------------------------------------------------------------
+    def forward_batch(self, rgb, net_w, net_h=None, out_hw=None):
+        """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] (what estimateleres returns; invert = True)."""
+        import torch
+        ops, w, L = self.ops, self.w, self.ops.L
+        st = _lib.stream_ptr
+        A = _lib
+        B, H, W, _ = rgb.shape
+        net_h = net_h if net_h is not None else net_w
+        if net_w % 32 or net_h % 32:
+            raise ValueError("LeReS needs a net size that is a multiple of 32")
+        # stem: pre-processing + im2col of the 7x7 / 2 conv, folded BN + ReLU in the GEMM, max-pool
+        h1, w1 = (net_h + 6 - 7) // 2 + 1, (net_w + 6 - 7) // 2 + 1
+        cols = self._buf('stem_cols', (B * h1 * w1, 192))
+        m = (ctypes.c_float * 3)(*self.MEAN)
+        s = (ctypes.c_float * 3)(*self.STD)
+        _lib.check(L.dm_leres_stem_im2col(rgb.data_ptr(), B, H, W, net_h, net_w, m, s, cols.data_ptr(), st()), "dm_leres_stem_im2col")
+        x = self._buf('stem', (B, h1, w1, 64))
+        ops.gemm(cols, 192, w['stem'][0], 192, B * h1 * w1, 64, 192, act=A.ACT_RELU, bias=w['stem'][1], C=x, ldc=64)
+        h, wd = (h1 + 2 - 3) // 2 + 1, (w1 + 2 - 3) // 2 + 1
+        xp = self._buf('pool', (B, h, wd, 64))
+        _lib.check(L.dm_maxpool3x3s2_nhwc_f16(x.data_ptr(), B, h1, w1, 64, xp.data_ptr(), st()), "dm_maxpool3x3s2_nhwc_f16")
+        ops.launches += 2
+        x, cin = xp, 64
+        feats = []
+        bi_global = 0
+        for li, nb in enumerate(self.LAYERS, start=1):
+            for bi in range(nb):
+                blk = w['blocks'][bi_global]
+                tag = f"l{li}b{bi % 2}" if bi > 0 else f"l{li}first"
+                width, cout, stride = blk['width'], blk['cout'], blk['stride']
+                M = B * h * wd
+                t1 = self._buf(tag + '_t1', (B, h, wd, width))
+                ops.gemm(x, cin, blk['c1'][0], cin, M, width, cin, act=A.ACT_RELU, bias=blk['c1'][1], C=t1, ldc=width)
+                if stride == 1:
+                    ho, wo = h, wd
+                    t2 = self._buf(tag + '_t2', (B, ho, wo, width))
+                    ops.conv3x3(t1, B, h, wd, width, blk['c2'][0], width, act=A.ACT_RELU, bias=blk['c2'][1], C=t2)
+                else:
+                    ho, wo = (h + 2 - 3) // 2 + 1, (wd + 2 - 3) // 2 + 1
+                    c2 = self._buf(tag + '_cols', (B * ho * wo, 9 * width))
+                    ops.im2col_s2(t1, B, h, wd, width, c2)
+                    t2 = self._buf(tag + '_t2', (B, ho, wo, width))
+                    ops.gemm(c2, 9 * width, blk['c2'][0], 9 * width, B * ho * wo, width, 9 * width, act=A.ACT_RELU, bias=blk['c2'][1], C=t2, ldc=width)
+                Mo = B * ho * wo
+                if blk['down'] is not None:
+                    xs = x
+                    if stride == 2:
+                        xs = self._buf(tag + '_xs', (B, ho, wo, cin))
+                        _lib.check(L.dm_subsample2_nhwc_f16(x.data_ptr(), B, h, wd, cin, xs.data_ptr(), st()), "dm_subsample2_nhwc_f16")
+                        ops.launches += 1
+                    idn = self._buf(tag + '_idn', (B, ho, wo, cout))
+                    ops.gemm(xs, cin, blk['down'][0], cin, Mo, cout, cin, bias=blk['down'][1], C=idn, ldc=cout)
+                else:
+                    idn = x
+                pre = self._buf(tag + '_pre', (B, ho, wo, cout))
+                last = bi == nb - 1
+                out = self._buf(f"feat{li}" if last else tag + '_out', (B, ho, wo, cout))
+                ops.gemm(t2, width, blk['c3'][0], width, Mo, cout, width, bias=blk['c3'][1], C=pre, ldc=cout, C2=out, R=idn, ldr=cout)
+                x, cin, h, wd = out, cout, ho, wo
+                bi_global += 1
+            feats.append((x, h, wd, cin))
+
+        def conv(name, xin, hh, ww, ci, wb, co, act=A.ACT_NONE, R=None, C2=False):
+            outp = self._buf(name, (B, hh, ww, co))
+            out2 = self._buf(name + '_r', (B, hh, ww, co)) if C2 else None
+            ops.conv3x3(xin, B, hh, ww, ci, wb[0], co, act=act, bias=wb[1], C=outp, C2=out2, R=R)
+            return out2 if C2 else outp
+
+        def ftb(name, xin, hh, ww, ci, f, cm):
+            x1 = conv(name + '_x1', xin, hh, ww, ci, f['c1'], cm, act=A.ACT_RELU)           # the in-place ReLU also rewrites the skip operand
+            b1 = conv(name + '_b1', x1, hh, ww, cm, f['b1'], cm, act=A.ACT_RELU)
+            return conv(name + '_o', b1, hh, ww, cm, f['b4'], cm, R=x1, C2=True)             # relu(x1 + branch)
+
+        def up2(name, xin, hh, ww, c):
+            outp = self._buf(name, (B, 2 * hh, 2 * ww, c))
+            ops.resize_nhwc(xin, B, hh, ww, c, outp, 2 * hh, 2 * ww)
+            return outp
+
+        f3, h3, w3, c3 = feats[3]
+        x = ftb('dconv', f3, h3, w3, c3, w['conv'], 512)
+        x = conv('dconv1', x, h3, w3, 512, w['conv1'], 256)
+        x = up2('up32', x, h3, w3, 256)
+        hh, ww = 2 * h3, 2 * w3
+        for k, fi in (('ffm2', 2), ('ffm1', 1), ('ffm0', 0)):
+            low, hl, wl, cl = feats[fi]
+            assert (hl, wl) == (hh, ww)
+            a1 = ftb(k + 'a', low, hl, wl, cl, w[k][0], 256)
+            sm = self._buf(k + '_sum', (B, hl, wl, 256))
+            _lib.check(L.dm_add_f16(a1.data_ptr(), x.data_ptr(), sm.data_ptr(), sm.numel(), st()), "dm_add_f16")
+            ops.launches += 1
+            x = ftb(k + 'b', sm, hl, wl, 256, w[k][1], 256)
+            x = up2(k + '_up', x, hl, wl, 256)
+            hh, ww = 2 * hl, 2 * wl
+        x = conv('ao0', x, hh, ww, 256, w['ao0'], 128, act=A.ACT_RELU)
+        d32 = self._buf('ao3', (B * hh * ww, 32), torch.float32)
+        ops.conv3x3(x, B, hh, ww, 128, w['ao3'][0], 32, epi=A.EPI_STORE_F32, bias=w['ao3'][1], X=d32, ldx=32)
+        dn = self._buf('dnet', (B, 2 * hh, 2 * ww), torch.float32)
+        _lib.check(L.dm_resize_f32_ld(d32.data_ptr(), 32, B, hh, ww, dn.data_ptr(), 2 * hh, 2 * ww, 0, st()), "dm_resize_f32_ld")
+        oh, ow = out_hw if out_hw is not None else (H, W)
+        out = torch.empty(B, oh, ow, dtype=torch.float32, device=self.device)
+        if (oh, ow) == (2 * hh, 2 * ww):
+            out.copy_(dn)                                      # cv2.resize to the same size is a copy
+        else:
+            ops.resize_f32(dn, B, 2 * hh, 2 * ww, out, oh, ow, 1)   # cv2.INTER_CUBIC (A = -0.75, replicated borders)
+        ops.launches += 2
+        return out
+
+    def to(self, device):
+        return self
+
+
 class NativeDepthModel:
     """Thin caller of the model-level C-ABI (include/depthmap_b200.h: dm_model_create / dm_depth_forward / dm_model_destroy,
     csrc/model.cu): the handle owns the packed weights, the activation buffers, the resolution tables and a captured CUDA
@@ -1060,6 +1273,17 @@ class ModelHolder:
                 if "optimizer" in sd:       # dmidas/base_model.py:13: training checkpoints wrap the weights
                     sd = sd["model"]
             model = NativeDepthModel(sd, model_type, torch.device(device))
+        elif model_type == 0:  # res101 (LeReS)
+            if self.weights_provider is not None:
+                sd = self.weights_provider(model_type)
+            else:
+                model_path = "./models/leres/res101.pth"
+                if not os.path.exists(model_path):
+                    raise FileNotFoundError(f"{model_path} not found (depthmap_b200 does not download checkpoints)")
+                sd = torch.load(model_path, map_location='cpu')
+                if "depth_model" in sd:      # src/depthmap_generation.py:113-116: strip_prefix_if_present(checkpoint['depth_model'], "module.")
+                    sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd["depth_model"].items()}
+            model = LeresEngine(sd, torch.device(device))
         elif model_type == 3:  # dpt_large_384 (MiDaS 3.0)
             if self.weights_provider is not None:
                 sd = self.weights_provider(model_type)
@@ -1084,7 +1308,7 @@ class ModelHolder:
             model = ZoeDepthNKEngine(sd, torch.device(device))
         else:
             raise NotImplementedError(f"model_type {model_type} is not implemented in depthmap_b200 yet "
-                                      f"(implemented: 1, 2 = DPT-BEiT-L 512/384; 3 = DPT-Large 384; 9 = ZoeDepth-NK; 12, 13, 14 = Depth-Anything-V2 S/B/L)")
+                                      f"(implemented: 0 = LeReS res101; 1, 2 = DPT-BEiT-L 512/384; 3 = DPT-Large 384; 9 = ZoeDepth-NK; 12, 13, 14 = Depth-Anything-V2 S/B/L)")
         self.depth_model = model
         self.depth_model_type = model_type
         self.resize_mode = "minimal"
@@ -1134,7 +1358,7 @@ class ModelHolder:
         """uint8 CUDA [B,H,W,3] -> (float32 CUDA [B,H,W], invert flag).  Batched form of get_raw_prediction."""
         if self.depth_model is None:
             raise RuntimeError("no depth model loaded; call ensure_models first")
-        if self.depth_model_type in (1, 2, 3, 9, 12, 13, 14):
+        if self.depth_model_type in (0, 1, 2, 3, 9, 12, 13, 14):
             pred = self.depth_model.forward_batch(rgb, net_width, net_height)
         else:
             raise NotImplementedError(f"model_type {self.depth_model_type}")

@@ -168,6 +168,25 @@ def leres_reference():
     return model, {k: v.detach().clone() for k, v in model.state_dict().items()}
 
 
+def test_leres_synthetic_state_dict_matches_reference_module():
+    """oracle.synth_weights.make_leres_state_dict has exactly the reference module's keys and shapes (strict load, only the
+    BatchNorm step counters are left out) and the oracle reproduces the reference module with it."""
+    import torch
+    ref_loader.bootstrap()
+    from lib.multi_depth_model_woauxi import RelDepthModel
+    from oracle import leres, synth_weights
+    sd = synth_weights.make_leres_state_dict(seed=2)
+    model = RelDepthModel(backbone="resnext101").eval()
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.endswith("num_batches_tracked") for k in res.missing_keys)
+    x = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        want = model.depth_model(x)
+        got = leres.forward(sd, x)
+    assert torch.isfinite(want).all() and want.abs().max().item() > 1e-3
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+
+
 def test_leres_network_oracle_equals_reference(leres_reference):
     import torch
     from oracle import leres
@@ -192,10 +211,15 @@ def test_leres_estimate_equals_reference(leres_reference):
     except Exception as e:
         pytest.skip(f"src.depthmap_generation not importable here: {e}")
     dg.depthmap_device = torch.device("cpu")
-    img = synth_rgb(70, 90, 3)
+    import cv2
+    rgb = synth_rgb(70, 90, 3)
+    img = cv2.cvtColor(rgb, cv2.COLOR_BGR2RGB) / 255.0       # what ModelHolder.get_raw_prediction hands over (:381)
     want = dg.estimateleres(img, model, 64, 96)
-    got, invert = leres.get_raw_prediction(img, sd, 64, 96)
+    got, invert = leres.get_raw_prediction(rgb, sd, 64, 96)
     assert invert is True and got.shape == want.shape == (70, 90)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    want = dg.estimateleres(rgb, model, 96, 64)               # and the function itself on a uint8 array
+    got = leres.estimateleres(rgb, sd, 96, 64)
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
 
 
