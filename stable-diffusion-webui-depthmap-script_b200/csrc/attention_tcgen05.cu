@@ -598,13 +598,32 @@ __device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (here P, fp16 pairs packed into 32-bit columns, lane = row) comes from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 __host__ __device__ __forceinline__ int attn4_nrd_pad(int nrd) { return ((nrd + 1 + 15) & ~31) + 16 >= nrd + 1 ? ((nrd + 1 + 15) & ~31) + 16 : ((nrd + 1 + 15) & ~31) + 48; }
 
-template <int BIAS_MODE>
+// PTMEM: P (the exponentiated tile) goes to TENSOR MEMORY instead of shared memory and the PV MMA reads it from there
+// (tcgen05.mma with the A operand in TMEM).  That removes the P stores, the proxy fence and the tensor core's re-read of P from
+// the shared-memory pipe, which the profile shows to be the busiest unit (bias loads + P stores + UMMA operand fetches).  TMEM is
+// then full — S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512) — so the ones block of the PV MMA
+// goes and each thread sums its 64 probabilities itself (the two halves of a row meet in the mailbox at the end).
+template <int BIAS_MODE, bool PTMEM>
 __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, Attn2Params pp) {
     const AttnParams &p = pp.a;
     constexpr bool ALIGNED = BIAS_MODE == 3;
+    constexpr int O_COL = 256, O_STRIDE = PTMEM ? 64 : A4_O_STRIDE, P_COL = 384;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *sQ = smem_raw + A4_Q_OFF, *sK = smem_raw + A4_K_OFF, *sV = smem_raw + A4_V_OFF, *sP = smem_raw + A4_P_OFF;
     uint8_t *sOnes = smem_raw + A4_ONES_OFF;
@@ -697,7 +716,8 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
             constexpr uint32_t idesc_pv = make_idesc_f16(AT_BQ, A2_PV_N, 0, 0, 1);
             const uint32_t ones_addr = smem_u32(sOnes);
             const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ + g * AT_Q_BYTES));
-            const uint32_t tmem_S = tmem_base + g * 128, tmem_O = tmem_base + A4_O_COL + g * A4_O_STRIDE;
+            const uint32_t tmem_S = tmem_base + g * 128, tmem_O = tmem_base + O_COL + g * O_STRIDE, tmem_P = tmem_base + P_COL + g * 64;
+            constexpr uint32_t idesc_pv_ts = make_idesc_f16(AT_BQ, AT_D, 0, 0, 1);
             mbar_wait_role(q_full, 0);
             for (int j = 0; j <= num_kv; ++j) {
                 if (j < num_kv) {      // S(j) = Q K_j^T as soon as K_j has landed and the softmax warps hold S(j-1) in registers
@@ -721,10 +741,13 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                     const uint32_t sv = smem_u32(sV + (jj & 1) * AT_KV_BYTES);
                     const int nk = tile_cols(jj) >> 4;
                     for (int k = 0; k < nk; ++k) {
-                        const uint64_t pdesc = make_desc_kmajor_sw128(sp + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32);
                         const uint32_t vaddr = sv + k * 16 * 128;
-                        const uint64_t vdesc = make_desc_mnmajor_sw128(vaddr, ones_addr - vaddr);
-                        umma_f16(tmem_O, pdesc, vdesc, idesc_pv, (jj != 0 || k != 0) ? 1u : 0u);
+                        if (PTMEM) {
+                            umma_f16_ts(tmem_O, tmem_P + k * 8, make_desc_mnmajor_sw128(vaddr, 8192), idesc_pv_ts, (jj != 0 || k != 0) ? 1u : 0u);
+                        } else {
+                            const uint64_t pdesc = make_desc_kmajor_sw128(sp + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32);
+                            umma_f16(tmem_O, pdesc, make_desc_mnmajor_sw128(vaddr, ones_addr - vaddr), idesc_pv, (jj != 0 || k != 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&pv_full[g]);
                     umma_commit(&v_empty[jj & 1]);
@@ -741,7 +764,9 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const uint32_t tmem_S = tmem_base + g * 128 + lane_off + hh * 64;
-        const uint32_t tmem_O = tmem_base + A4_O_COL + g * A4_O_STRIDE + lane_off;
+        const uint32_t tmem_O = tmem_base + O_COL + g * O_STRIDE + lane_off;
+        const uint32_t tmem_P = tmem_base + P_COL + g * 64 + lane_off + hh * 32;     // PTMEM: this thread's 64 probabilities = 32 packed columns
+        float l_run = 0.f;                                                            // PTMEM: sum of this thread's probabilities
         uint8_t *p_row = sP + g * AT_P_BYTES + hh * (AT_BQ * 128) + row * 128;   // this thread's 64 columns = one swizzle atom row
         const uint32_t sw = (uint32_t)(row & 7) << 4;
         const int pair_bar = 1 + g * 4 + q;
@@ -897,7 +922,8 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                         tmem_st_32x16(tmem_O + hh * 32 + c * 16, o);
                     }
-                    if (hh == 0) {
+                    if (PTMEM) l_run *= alpha;
+                    else if (hh == 0) {
                         const uint32_t rs = tmem_ld_32x1(tmem_O + 64);
                         tmem_ld_wait();
                         tmem_st_32x1(tmem_O + 64, __float_as_uint(__uint_as_float(rs) * alpha));
@@ -909,13 +935,21 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
             if (token) { if (g == 0) asm volatile("bar.sync 9, 512;" ::: "memory"); else asm volatile("bar.sync 10, 512;" ::: "memory"); }
             auto emit = [&](int c) {
                 uint32_t packed[8];
+                float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const __half2 h2 = __floats2half2_rn(ex2_approx(__uint_as_float(r[c * 16 + i])), ex2_approx(__uint_as_float(r[c * 16 + i + 1])));
+                    const float e0 = ex2_approx(__uint_as_float(r[c * 16 + i])), e1 = ex2_approx(__uint_as_float(r[c * 16 + i + 1]));
+                    if (PTMEM) { ls0 += e0; ls1 += e1; }
+                    const __half2 h2 = __floats2half2_rn(e0, e1);
                     packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
                 }
-                *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c) << 4) ^ sw)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c + 1) << 4) ^ sw)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                if (PTMEM) {
+                    l_run += ls0 + ls1;
+                    tmem_st_32x8(tmem_P + c * 8, packed);
+                } else {
+                    *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c) << 4) ^ sw)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4 *>(p_row + (((uint32_t)(2 * c + 1) << 4) ^ sw)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
             };
             if (nmine == 64) {
 #pragma unroll
@@ -926,7 +960,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                     if (c * 16 < nmine) emit(c);
             }
             if (token) { if (g == 0) asm volatile("bar.arrive 10, 512;" ::: "memory"); else if (j + 1 < num_kv) asm volatile("bar.arrive 9, 512;" ::: "memory"); }
-            fence_proxy_async();
+            if (PTMEM) tmem_st_wait(); else fence_proxy_async();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g]);
@@ -936,10 +970,18 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
         {
             uint32_t o[32];
             tmem_ld_32x32(tmem_O + hh * 32, o);
-            const uint32_t rs = tmem_ld_32x1(tmem_O + 64);
+            uint32_t rs = 0;
+            if (!PTMEM) rs = tmem_ld_32x1(tmem_O + 64);
             tmem_ld_wait();
+            float total = __uint_as_float(rs);
+            if (PTMEM) {                                   // the row's sum = this half's + the other half's (same mailbox as the maxima)
+                float *slot = s_xch + (((xch_n & 1) * 2 + g) * 128 + row) * 2;
+                slot[hh] = l_run;
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                total = l_run + slot[hh ^ 1];
+            }
             if (q_ok) {
-                const float inv = 1.0f / __uint_as_float(rs);
+                const float inv = 1.0f / total;
                 __half *dst = p.out + (size_t)(row_base + qi) * p.C + h * AT_D + hh * 32;
 #pragma unroll
                 for (int d = 0; d < AT_D / 2; d += 8) {
@@ -981,10 +1023,19 @@ static int launch_attn4(const CUtensorMap &tm, const Attn2Params &pp, cudaStream
     } else {
         const size_t tab = attn4_table_bytes(MODE, pp.nrd, pp.a.N, num_main, num_kv);
         if (tab > (size_t)A4_TAB_MAX) { set_error("attention: relative-position table (%d entries) does not fit in shared memory", pp.nrd); return DM_E_UNSUPPORTED; }
-        static PerDeviceFlag configured;
-        if (!configured.test_and_set())
-            DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd4_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_MAX));
-        attention_fwd4_kernel<MODE><<<grid, A4_THREADS, A4_TAB_OFF + tab, stream>>>(tm, pp);
+        static int p_tmem = -1;       // DEPTHMAP_B200_ATTN_PTMEM=0: P through shared memory (the first fwd4 form), kept for A/B timing
+        if (p_tmem < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_PTMEM"); p_tmem = (e && e[0] == '0') ? 0 : 1; }
+        if (p_tmem) {
+            static PerDeviceFlag configured;
+            if (!configured.test_and_set())
+                DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd4_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_MAX));
+            attention_fwd4_kernel<MODE, true><<<grid, A4_THREADS, A4_TAB_OFF + tab, stream>>>(tm, pp);
+        } else {
+            static PerDeviceFlag configured;
+            if (!configured.test_and_set())
+                DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd4_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_MAX));
+            attention_fwd4_kernel<MODE, false><<<grid, A4_THREADS, A4_TAB_OFF + tab, stream>>>(tm, pp);
+        }
         DM_LAUNCH_CHECK("attention_fwd4_kernel");
     }
     if (MODE == 3) {
