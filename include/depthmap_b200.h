@@ -53,6 +53,8 @@ int dm_normalize_u16(const float *pred, int B, int H, int W, int invert, int cli
  * per percentile: ranks[0..1] / ranks[2..3] are the 0-based ranks (ascending, after the optional sign flip) of the far /
  * near percentile and gamma_far / gamma_near the float64 interpolation weights; both depend only on H*W and the two
  * fractions and are computed by the host face with numpy's own expression (core.percentile_plan). */
+/* convert_to_i16 (src/core.py:44-50) of float64 values in [0, 1) (custom depth maps, src/core.py:146-174) */
+int dm_convert_to_i16_f64(const double *x, long long n, uint16_t *out, void *stream);
 size_t dm_normalize_u16_outliers_workspace_bytes(int B);
 int dm_normalize_u16_outliers(const float *pred, int B, int H, int W, int invert, const int64_t ranks[4], double gamma_far,
                               double gamma_near, uint16_t *depth_out, int32_t *degenerate_flags, void *workspace,
@@ -92,6 +94,13 @@ typedef struct dm_stereo_params {
     int64_t dst_img_stride[2];
 } dm_stereo_params;
 
+/* The other packings of create_stereoimages (:56-73) from a left | right pair sbs [B,H,2W,3]: mode 0 left-right, 1 right-left,
+ * 2 top-bottom, 3 bottom-top, 4 red-cyan-anaglyph, 5 left-only, 6 only-right, 7 cyan-red-reverseanaglyph (a request with several
+ * modes computes the eyes once and packs each mode with this). */
+int dm_stereo_pack(const uint8_t *sbs, int B, int H, int W, int mode, uint8_t *out, void *stream);
+/* apply_stereo_divergence's (d - min) / (max - min) (:79-81) for depth maps that are not uint16, in numpy's dtype rules
+ * (dtype 0 float32, 1 float64, 2 int64) -> float64 [B, n] for DM_DEPTH_ND64; flat_out (optional): 1 where max == min */
+int dm_depth_to_nd64(const void *depth, int dtype, int B, long long n, double *nd_out, int32_t *flat_out, void *stream);
 size_t dm_stereo_workspace_bytes(int B, int H, int W);
 int dm_stereo(const uint8_t *rgb, const void *depth, int B, int H, int W, const dm_stereo_params *params_host,
               uint8_t *out0, uint8_t *out1, void *workspace, size_t workspace_bytes, void *stream);

@@ -68,7 +68,7 @@ _lib = None
 EXPORTS = [
     "dm_last_error", "dm_version", "dm_device_name",
     "dm_normalize_u16_workspace_bytes", "dm_normalize_u16", "dm_normalize_u16_outliers_workspace_bytes", "dm_normalize_u16_outliers",
-    "dm_stereo_workspace_bytes", "dm_stereo",
+    "dm_stereo_workspace_bytes", "dm_stereo", "dm_stereo_pack", "dm_depth_to_nd64", "dm_convert_to_i16_f64",
     "dm_normalmap_workspace_bytes", "dm_normalmap",
     "dm_gemm_ex", "dm_conv3x3_ex", "dm_gemm_f16", "dm_conv3x3_f16", "dm_attention_f16", "dm_attention_relpos_f16", "dm_preprocess_patchify",
     "dm_assemble_tokens", "dm_layernorm_f16", "dm_resize_bilinear_nhwc_f16", "dm_resize_f32", "dm_im2col_s2_f16", "dm_concat_readout_f16",
@@ -105,6 +105,9 @@ def load() -> ctypes.CDLL:
         L.dm_stereo_workspace_bytes.argtypes = [i32, i32, i32]
         L.dm_stereo_workspace_bytes.restype = sz
         L.dm_stereo.argtypes = [vp, vp, i32, i32, i32, c.POINTER(StereoParams), vp, vp, vp, sz, vp]
+        L.dm_stereo_pack.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+        L.dm_depth_to_nd64.argtypes = [vp, i32, i32, c.c_longlong, vp, vp, vp]
+        L.dm_convert_to_i16_f64.argtypes = [vp, c.c_longlong, vp, vp]
         L.dm_normalmap_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
         L.dm_normalmap_workspace_bytes.restype = sz
         L.dm_normalmap.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]

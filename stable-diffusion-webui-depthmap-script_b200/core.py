@@ -167,6 +167,9 @@ def convert_to_i16(arr):
     import torch
     dev = _lib.require_cuda()
     a = np.asarray(arr)
+    if a.dtype == np.float64:
+        return convert_to_i16_batch(torch.from_numpy(np.ascontiguousarray(a)).to(dev)).cpu().numpy()
+    # float32 input: numpy keeps float32 arithmetic (Python scalars are weakly typed)
     t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     max_val = 2 ** 16
     out = torch.clamp(t * max_val + 0.0001, 0, max_val - 0.1)
@@ -175,10 +178,12 @@ def convert_to_i16(arr):
 
 def convert_to_i16_batch(t):
     """float64 CUDA tensor in [0, 1) -> uint16 CUDA tensor; the arithmetic of src/core.py:44-50 in float64 (what numpy
-    does for the float64 custom depth maps of src/core.py:146-174)."""
+    does for the float64 custom depth maps of src/core.py:146-174) — dm_convert_to_i16_f64."""
     import torch
-    q = torch.clamp(t.to(torch.float64) * 65536 + 0.0001, 0, 65536 - 0.1).to(torch.int32)
-    return q.to(torch.int16).view(torch.uint16)  # values < 65536: the int16 wrap is the uint16 bit pattern
+    t = t.to(torch.float64).contiguous()
+    out = torch.empty(t.shape, dtype=torch.uint16, device=t.device)
+    _lib.check(_lib.load().dm_convert_to_i16_f64(t.data_ptr(), t.numel(), out.data_ptr(), _lib.stream_ptr()), "dm_convert_to_i16_f64")
+    return out
 
 
 def convert_i16_to_rgb(image, like):

@@ -455,3 +455,23 @@ DM_EXPORT int dm_video_scale_f64(const float *x, long long n, const double *ab, 
     DM_LAUNCH_CHECK("video_scale_f64_kernel");
     return DM_OK;
 }
+
+// convert_to_i16 (src/core.py:44-50) for the float64 values of a custom depth map (src/core.py:146-174): numpy evaluates
+// clip(x * 65536 + 0.0001, 0, 65535.9) in float64 and truncates
+namespace dm {
+__global__ void __launch_bounds__(256) convert_to_i16_f64_kernel(const double *__restrict__ x, long long n, uint16_t *__restrict__ out) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        double q = __dadd_rn(__dmul_rn(__ldg(x + i), 65536.0), 0.0001);
+        q = fmin(fmax(q, 0.0), 65535.9);
+        out[i] = (q == q) ? (uint16_t)(int)q : (uint16_t)0;
+    }
+}
+}  // namespace dm
+DM_EXPORT int dm_convert_to_i16_f64(const double *x, long long n, uint16_t *out, void *stream_) {
+    using namespace dm;
+    if (!x || !out || n <= 0) { set_error("dm_convert_to_i16_f64: bad arguments"); return DM_E_INVALID; }
+    convert_to_i16_f64_kernel<<<video_grid(n), 256, 0, (cudaStream_t)stream_>>>(x, n, out);
+    DM_LAUNCH_CHECK("convert_to_i16_f64_kernel");
+    return DM_OK;
+}

@@ -634,3 +634,100 @@ extern "C" __attribute__((visibility("default"))) int dm_stereo(const uint8_t *r
     DM_LAUNCH_CHECK("stereo_row_kernel");
     return DM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dm_stereo_pack — the packings of create_stereoimages (src/stereoimage_generation.py:56-73) from a side-by-side pair, for
+// requests with several modes: the eyes are computed once (left | right), every further mode is one byte-shuffling pass.
+// dm_depth_to_nd64 — apply_stereo_divergence's normalisation (:79-81) for depth maps that are not uint16: numpy evaluates
+// (d - min) / (max - min) in the array's own dtype (float32 stays float32, integers true-divide to float64); the result is
+// widened to the float64 the row kernels read.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace dm {
+
+__global__ void __launch_bounds__(256) stereo_pack_kernel(const uint8_t *__restrict__ sbs, int H, int W, int mode, uint8_t *__restrict__ out) {
+    // one thread per output pixel; blockIdx.y = output row, blockIdx.z = image
+    const int b = blockIdx.z;
+    const uint8_t *L = sbs + (size_t)b * H * 2 * W * 3;      // row y: [left eye W px | right eye W px]
+    int oh = H, ow = W;
+    if (mode == 0 || mode == 1) ow = 2 * W;
+    if (mode == 2 || mode == 3) oh = 2 * H;
+    const int y = blockIdx.y, x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= ow || y >= oh) return;
+    int sy = y, sxr = x, sxg = x;     // source column (in the 2W-wide pair) of the red and of the green / blue channel
+    switch (mode) {
+        case 0: break;                                                        // left-right
+        case 1: sxr = sxg = x < W ? x + W : x - W; break;                       // right-left
+        case 2: sy = y < H ? y : y - H; sxr = sxg = y < H ? x : x + W; break;   // top-bottom: left eye on top
+        case 3: sy = y < H ? y : y - H; sxr = sxg = y < H ? x + W : x; break;   // bottom-top
+        case 4: sxr = x; sxg = x + W; break;                                    // red-cyan anaglyph: R from the left eye, G B from the right
+        case 5: break;                                                        // left-only
+        case 6: sxr = sxg = x + W; break;                                       // only-right
+        default: sxr = x + W; sxg = x; break;                                   // cyan-red reverse anaglyph
+    }
+    const uint8_t *pr = L + ((size_t)sy * 2 * W + sxr) * 3, *pg = L + ((size_t)sy * 2 * W + sxg) * 3;
+    uint8_t *o = out + (((size_t)b * oh + y) * ow + x) * 3;
+    o[0] = pr[0]; o[1] = pg[1]; o[2] = pg[2];
+}
+
+template <typename T> struct NdTraits;
+template <> struct NdTraits<float> {
+    __device__ static bool less(float a, float b) { return a < b; }
+    __device__ static double norm(float x, float mn, float mx) { return (double)__fdiv_rn(__fsub_rn(x, mn), __fsub_rn(mx, mn)); }
+};
+template <> struct NdTraits<double> {
+    __device__ static bool less(double a, double b) { return a < b; }
+    __device__ static double norm(double x, double mn, double mx) { return __ddiv_rn(__dsub_rn(x, mn), __dsub_rn(mx, mn)); }
+};
+template <> struct NdTraits<long long> {
+    __device__ static bool less(long long a, long long b) { return a < b; }
+    __device__ static double norm(long long x, long long mn, long long mx) { return __ddiv_rn((double)(x - mn), (double)(mx - mn)); }
+};
+
+// one CTA per image (these maps are small next to the network; the uint16 fast path does not come here)
+template <typename T>
+__global__ void __launch_bounds__(1024) depth_to_nd64_kernel(const T *__restrict__ depth, long long n, double *__restrict__ nd, int32_t *flat) {
+    __shared__ T s_lo[32], s_hi[32];
+    const int b = blockIdx.x;
+    const T *p = depth + (size_t)b * n;
+    T lo = p[0], hi = p[0];
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) { const T v = p[i]; if (NdTraits<T>::less(v, lo)) lo = v; if (NdTraits<T>::less(hi, v)) hi = v; }
+    // NaNs: numpy's min / max propagate NaN; a NaN depth map is outside what the reference can render either — not reproduced
+    for (int o = 16; o > 0; o >>= 1) {
+        const T a = __shfl_xor_sync(0xffffffffu, lo, o), c = __shfl_xor_sync(0xffffffffu, hi, o);
+        if (NdTraits<T>::less(a, lo)) lo = a;
+        if (NdTraits<T>::less(hi, c)) hi = c;
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    lo = s_lo[0]; hi = s_hi[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { if (NdTraits<T>::less(s_lo[w], lo)) lo = s_lo[w]; if (NdTraits<T>::less(hi, s_hi[w])) hi = s_hi[w]; }
+    if (threadIdx.x == 0 && flat) flat[b] = (lo == hi) ? 1 : 0;
+    double *o = nd + (size_t)b * n;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) o[i] = NdTraits<T>::norm(p[i], lo, hi);
+}
+
+}  // namespace dm
+
+extern "C" __attribute__((visibility("default"))) int dm_stereo_pack(const uint8_t *sbs, int B, int H, int W, int mode, uint8_t *out, void *stream_) {
+    using namespace dm;
+    if (!sbs || !out || B <= 0 || H <= 0 || W <= 0 || mode < 0 || mode > 7) { set_error("dm_stereo_pack: bad arguments"); return DM_E_INVALID; }
+    const int oh = (mode == 2 || mode == 3) ? 2 * H : H, ow = (mode == 0 || mode == 1) ? 2 * W : W;
+    if (oh > 65535 || B > 65535) { set_error("dm_stereo_pack: shape too large"); return DM_E_UNSUPPORTED; }
+    stereo_pack_kernel<<<dim3((unsigned)((ow + 255) / 256), (unsigned)oh, (unsigned)B), 256, 0, (cudaStream_t)stream_>>>(sbs, H, W, mode, out);
+    DM_LAUNCH_CHECK("stereo_pack_kernel");
+    return DM_OK;
+}
+
+/* dtype: 0 float32, 1 float64, 2 int64.  nd_out float64 [B, n]; flat_out (optional) int32[B]: 1 where max == min */
+extern "C" __attribute__((visibility("default"))) int dm_depth_to_nd64(const void *depth, int dtype, int B, long long n, double *nd_out, int32_t *flat_out,
+                                                                    void *stream_) {
+    using namespace dm;
+    if (!depth || !nd_out || B <= 0 || n <= 0) { set_error("dm_depth_to_nd64: bad arguments"); return DM_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (dtype == 0) depth_to_nd64_kernel<float><<<B, 1024, 0, st>>>((const float *)depth, n, nd_out, flat_out);
+    else if (dtype == 1) depth_to_nd64_kernel<double><<<B, 1024, 0, st>>>((const double *)depth, n, nd_out, flat_out);
+    else if (dtype == 2) depth_to_nd64_kernel<long long><<<B, 1024, 0, st>>>((const long long *)depth, n, nd_out, flat_out);
+    else { set_error("dm_depth_to_nd64: dtype %d unsupported", dtype); return DM_E_UNSUPPORTED; }
+    DM_LAUNCH_CHECK("depth_to_nd64_kernel");
+    return DM_OK;
+}

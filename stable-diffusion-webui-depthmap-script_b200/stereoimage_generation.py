@@ -53,23 +53,27 @@ def _launch(rgb, depth, depth_kind, eyes, exponent, fill, pack, red_eye, out0, o
 
 
 def _prepare_depth(depth, poly):
-    """uint16 goes to the fused device path; anything else is normalised like numpy would (:79-81) into float64."""
+    """uint16 goes to the fused device path; anything else is normalised like numpy would (:79-81) into float64 by
+    dm_depth_to_nd64 (float32 / float64 / integer maps; float16 maps, which numpy would normalise in float16, are widened first)."""
     import torch
     if depth.dtype == torch.uint16:
         return depth.contiguous(), _lib.DM_DEPTH_U16, None
     B = depth.shape[0]
-    flat_mask = []
-    if depth.dtype in (torch.float32, torch.float64, torch.float16, torch.bfloat16):
+    if depth.dtype == torch.float32:
+        d, code = depth.contiguous(), 0
+    elif depth.dtype == torch.float64:
+        d, code = depth.contiguous(), 1
+    elif depth.dtype in (torch.float16, torch.bfloat16):
         mn = depth.reshape(B, -1).min(dim=1).values.view(B, 1, 1)
         mx = depth.reshape(B, -1).max(dim=1).values.view(B, 1, 1)
-        nd = ((depth - mn) / (mx - mn)).to(torch.float64)
+        return ((depth - mn) / (mx - mn)).to(torch.float64).contiguous(), _lib.DM_DEPTH_ND64, (mx == mn).view(B)
     else:
-        d = depth.to(torch.int64)
-        mn = d.reshape(B, -1).min(dim=1).values.view(B, 1, 1)
-        mx = d.reshape(B, -1).max(dim=1).values.view(B, 1, 1)
-        nd = (d - mn).to(torch.float64) / (mx - mn).to(torch.float64)
-    flat = (mx == mn).view(B)
-    return nd.contiguous(), _lib.DM_DEPTH_ND64, flat
+        d, code = depth.to(torch.int64).contiguous(), 2
+    n = d[0].numel()
+    nd = torch.empty(d.shape, dtype=torch.float64, device=d.device)
+    flat = torch.empty(B, dtype=torch.int32, device=d.device)
+    _lib.check(_lib.load().dm_depth_to_nd64(d.data_ptr(), code, B, n, nd.data_ptr(), flat.data_ptr(), _lib.stream_ptr()), "dm_depth_to_nd64")
+    return nd, _lib.DM_DEPTH_ND64, flat.bool()
 
 
 def create_stereoimages_batch(rgb, depth, divergence, separation=0.0, modes=None, stereo_balance=0.0,
@@ -133,24 +137,12 @@ def create_stereoimages_batch(rgb, depth, divergence, separation=0.0, modes=None
         if mode not in _MODES:
             raise Exception('Unknown mode')
         if not single or flat is not None and bool(flat.any()):
-            s = get_sbs()
-            Lt, Rt = s[:, :, :W, :], s[:, :, W:, :]
-            if mode == 'left-right':
-                results.append(s if single else s.clone())
-            elif mode == 'right-left':
-                results.append(torch.cat([Rt, Lt], dim=2))
-            elif mode == 'top-bottom':
-                results.append(torch.cat([Lt, Rt], dim=1))
-            elif mode == 'bottom-top':
-                results.append(torch.cat([Rt, Lt], dim=1))
-            elif mode == 'red-cyan-anaglyph':
-                results.append(torch.stack([Lt[..., 0], Rt[..., 1], Rt[..., 2]], dim=-1))
-            elif mode == 'cyan-red-reverseanaglyph':
-                results.append(torch.stack([Rt[..., 0], Lt[..., 1], Lt[..., 2]], dim=-1))
-            elif mode == 'left-only':
-                results.append(Lt.contiguous())
-            else:
-                results.append(Rt.contiguous())
+            s = get_sbs()                       # eyes computed once; every mode is one dm_stereo_pack pass over the pair
+            code = _MODES.index(mode)
+            oh, ow = (2 * H if code in (2, 3) else H), (2 * W if code in (0, 1) else W)
+            out = torch.empty((B, oh, ow, 3), dtype=torch.uint8, device=dev)
+            _lib.check(_lib.load().dm_stereo_pack(s.data_ptr(), B, H, W, code, out.data_ptr(), _lib.stream_ptr()), "dm_stereo_pack")
+            results.append(out)
             continue
         # single mode: the kernel writes the packed layout directly (compulsory traffic only)
         if mode in ('left-right', 'right-left'):

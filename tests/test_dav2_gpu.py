@@ -53,4 +53,4 @@ def test_modelholder_api(cuda_device):
     mh.offload(); mh.reload(); mh.unload_models()
     assert mh.depth_model is None
     with pytest.raises(NotImplementedError):
-        mh.ensure_models(0, cuda_device, False)
+        mh.ensure_models(4, cuda_device, False)      # dpt_hybrid_384: not implemented
