@@ -54,10 +54,11 @@ def test_beit_large_512_batch32(cuda_device):
             failures.append(str(e))
     assert np.array_equal(solo, got[0])
     # identical inputs at different batch positions give identical outputs
-    assert np.array_equal(got[0], got[3]) and np.array_equal(got[1], got[31])
+    assert np.array_equal(got[0], got[3]) and np.array_equal(got[1], got[30]) and np.array_equal(got[2], got[31])
     assert not failures, failures
 
 
+@pytest.mark.parametrize("hw,net", [((384, 384), (384, 384)), ((384, 512), (384, 384)), ((512, 768), (512, 512))])
 def test_beit_large_384_and_nonsquare(cuda_device, hw, net):
     """beitl16_384 at its native size, on a 4:3 image (net 512x384: generic relative-position mode, window 24 -> 24x32)
     and — ADVICE r1 — beitl16_512 on a 3:2 image (net 768x512, nrd = 5988 > 4096)."""

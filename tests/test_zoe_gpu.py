@@ -35,7 +35,7 @@ def test_zoedepth_tiny_core_vs_oracle(cuda_device, seed, hw, net):
         want, invert = ozd.get_raw_prediction(img, sd, net[0], net[1], core_name='beit_tiny')
         assert invert is True and want.max() - want.min() > 0.05
         ref16 = precision.reference_fp16_error_zoe(img, sd, net[0], net[1], 'beit_tiny', want, cuda_device)
-        precision.check(f"zoedepth_nk tiny seed{seed} {hw} net {net} img{i}", got[i], want, ref16)
+        precision.check(f"zoedepth_nk tiny seed{seed} {hw} net {net} img{i}", got[i], want, ref16, slack=1.5)
 
 
 def test_zoedepth_nk_beit384_core(cuda_device):
