@@ -285,3 +285,99 @@ def test_dav2_oracle_equals_reference(encoder, hw, net):
     assert want.max() - want.min() > 0.1          # a non-degenerate map (default init would be identically zero)
     assert got.shape == want.shape == tuple(hw)
     assert float(np.abs(got - want).max()) <= 1e-6 * float(np.abs(want).max()), float(np.abs(got - want).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# D9: the BOOST driver (resolution search, patch selection, double estimation, merge + blend) against the reference's own
+# functions.  The two networks are stand-ins (cheap, deterministic, the same on both sides): the real ones are pinned above.
+# ---------------------------------------------------------------------------------------------------------------------
+class _FakeLeres:
+    """stands for RelDepthModel: estimateleres calls model.depth_model(normalised [1,3,h,w])"""
+
+    @staticmethod
+    def depth_model(x):
+        import torch
+        import torch.nn.functional as F
+        g = x.mean(dim=1, keepdim=True)
+        return F.avg_pool2d(g, 9, 1, 4) + 0.25 * torch.sin(3.0 * x[:, :1]) + 0.1 * x[:, 2:3]
+
+
+class _FakePix2Pix:
+    """stands for Pix2Pix4DepthModel: set_input / test / get_current_visuals (pix2pix/models/pix2pix4depth_model.py:96-116)"""
+
+    def set_input(self, outer, inner):
+        from oracle import pix2pix as op2p
+        self.real_A = op2p.merge_input(outer, inner)
+
+    def test(self):
+        import torch
+        o, i = self.real_A[:, :1], self.real_A[:, 1:]
+        self.fake_B = torch.tanh(0.7 * o + 0.5 * i + 0.1 * o * i)
+
+    def get_current_visuals(self):
+        return {"fake_B": self.fake_B}
+
+
+def _boost_reference_module():
+    import torch
+    ref_loader.bootstrap()
+    try:
+        from src import depthmap_generation as dg
+    except Exception as e:
+        pytest.skip(f"src.depthmap_generation not importable here: {e}")
+    dg.depthmap_device = torch.device("cpu")
+    import skimage.measure as sm
+    from oracle import boost
+    sm.block_reduce = lambda img, block, func: boost.block_reduce_max(img, block[0])   # skimage is absent here (SURVEY A.5); zero-padded max pool
+    dg.skimage = __import__("skimage")
+    return dg
+
+
+def _fake_estimate(img, msize):
+    import cv2
+    from oracle import leres
+    with __import__("torch").no_grad():
+        pred = _FakeLeres.depth_model(leres.preprocess(img, msize, msize)).squeeze().numpy()
+    return cv2.resize(pred, (img.shape[1], img.shape[0]), interpolation=cv2.INTER_CUBIC)
+
+
+def _fake_merge(outer, inner):
+    p = _FakePix2Pix()
+    p.set_input(outer, inner)
+    p.test()
+    return p.fake_B.squeeze().numpy()
+
+
+@pytest.mark.parametrize("hw,rmax", [((300, 420), 1600), ((520, 360), 1200)])
+def test_boost_selection_equals_reference(hw, rmax):
+    """calculateprocessingres + generatepatchs + generatemask: integer / index results, compared exactly."""
+    import cv2
+    from oracle import boost
+    dg = _boost_reference_module()
+    rgb = synth_rgb(hw[0], hw[1], 11)
+    img = cv2.cvtColor(rgb, cv2.COLOR_BGR2RGB) / 255.0
+    want = dg.calculateprocessingres(img, 448, 0.2, 3, rmax)
+    got = boost.calculateprocessingres(img, 448, 0.2, 3, rmax)
+    assert got[0] == want[0] and got[1] == want[1]
+    factor = max(min(1, 4 * got[1] * got[0] / rmax), 0.2)
+    a, b = boost.target_size(img.shape, got[0], factor)
+    big = cv2.resize(img, (b, a), interpolation=cv2.INTER_CUBIC)
+    wantp = dg.generatepatchs(big, 896, factor)
+    gotp = boost.generatepatchs(big, 896, factor)
+    assert len(gotp) == len(wantp) and len(gotp) > 0
+    assert [kv[1]["rect"] for kv in gotp] == [list(kv[1]["rect"]) for kv in wantp]
+    assert np.array_equal(boost.generatemask((300, 300)), dg.generatemask((300, 300)))
+
+
+def test_boost_estimate_equals_reference():
+    """estimateboost end to end (model type 0: receptive field 448, patches at 896) with the stand-in networks."""
+    import cv2
+    from oracle import boost
+    dg = _boost_reference_module()
+    rgb = synth_rgb(300, 420, 12)
+    img = cv2.cvtColor(rgb, cv2.COLOR_BGR2RGB) / 255.0
+    want = dg.estimateboost(img.copy(), _FakeLeres(), 0, _FakePix2Pix(), 1600)
+    info = {}
+    got = boost.estimateboost(img.copy(), 0, _fake_estimate, _fake_merge, 1600, info=info)
+    assert got.shape == want.shape == (300, 420) and len(info["patches"]) >= 2
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
