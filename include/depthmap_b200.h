@@ -283,6 +283,34 @@ int dm_add_f16(const void *a, const void *b, void *out, long long n, void *strea
 /* dm_resize_f32 reading pixel (y, x) at in[(y * Win + x) * ld] (channel 0 of an [pixels, ld] fp32 GEMM output) */
 int dm_resize_f32_ld(const float *in, int ld, int B, int Hin, int Win, float *out, int Hout, int Wout, int mode, void *stream);
 
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * D9 — BOOST (csrc/boost_kernels.cu): the device side of estimateboost / doubleestimate
+ * (src/depthmap_generation.py:774-941, :1028-1050) and of the pix2pix merge U-Net (pix2pix/models/networks.py:444-543,
+ * pix2pix/models/pix2pix4depth_model.py:96-116).  The U-Net keeps fp32 NHWC activations; `split` != 0 makes the column
+ * builders emit [hi | lo | hi] fp16 triples (3 K columns) for the split-operand GEMM (weights packed [hi | hi | lo]).
+ * Reductions leave dm_boost_partials() partial results in device memory that the consuming kernel folds itself.
+ * ------------------------------------------------------------------------------------------------------------- */
+int dm_boost_partials(void);
+int dm_unet_first_cols(const float *x /*[H,W,2]*/, int H, int W, void *out /*fp16 [H/2*W/2, 64 (*3)]*/, int split, void *stream);
+int dm_unet_down_cols(const float *x /*[H,W,C]*/, int H, int W, int C, void *out /*fp16 [H/2*W/2, 16C (*3)]*/, int split, void *stream);
+int dm_unet_up_cols(const float *skip, int C1, const float *up, int C2, int H, int W, void *out /*fp16 [4][H*W, 4(C1+C2) (*3)]*/, int split,
+                    void *stream);
+int dm_unet_interleave(const float *tmp /*[4][H*W,N]*/, int H, int W, int N, int C, float *out /*[2H,2W,C]*/, void *stream);
+int dm_unet_final(const float *tmp /*[4][H*W,N]*/, int H, int W, int N, float bias, float *out /*[2H,2W]*/, void *stream);
+int dm_boost_minmax(const float *x, long long n, float *partial /*[partials][2]*/, void *stream);
+int dm_boost_merge_input(const float *outer, const float *inner, long long n, const float *p_outer, const float *p_inner, float *out /*[n,2]*/,
+                         void *stream);
+int dm_boost_post(const float *t, long long n, const float *partial, int normalise, float *out, void *stream);
+int dm_boost_fit_sums(const float *x, const float *y, long long n, double *partial /*[partials][4]*/, void *stream);
+int dm_boost_blend(const float *mapped /*[S,S]*/, int S, const double *fit_partial, const float *profile, int n_profile, float *updated, int pitch,
+                   int x1, int y1, int w, int h, void *stream);
+int dm_boost_resize_cubic(const float *in, int in_pitch, long long in_plane, int Hin, int Win, float *out, int out_pitch, long long out_plane,
+                          int Hout, int Wout, int planes, void *stream);
+int dm_boost_u8_to_planar(const uint8_t *rgb /*[H,W,3]*/, int H, int W, float *out /*[3,H,W] = rgb / 255*/, void *stream);
+int dm_leres_stem_im2col_f32(const float *img /*[3,Hi,Wi]*/, int Hi, int Wi, int x0, int y0, int w, int h, int net_h, int net_w, const float *mean,
+                             const float *std, void *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

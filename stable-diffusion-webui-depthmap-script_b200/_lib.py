@@ -78,6 +78,9 @@ EXPORTS = [
     "dm_video_select_pick", "dm_video_select_bounds", "dm_video_scale_f64",
     "dm_model_create", "dm_model_destroy", "dm_model_net_size", "dm_model_launches", "dm_depth_forward", "dm_dinov2_pos_embed", "dm_beit_rel_table", "dm_vit_pos_embed",
     "dm_leres_stem_im2col", "dm_maxpool3x3s2_nhwc_f16", "dm_subsample2_nhwc_f16", "dm_add_f16", "dm_resize_f32_ld",
+    "dm_boost_partials", "dm_unet_first_cols", "dm_unet_down_cols", "dm_unet_up_cols", "dm_unet_interleave", "dm_unet_final", "dm_boost_minmax",
+    "dm_boost_merge_input", "dm_boost_post", "dm_boost_fit_sums", "dm_boost_blend", "dm_boost_resize_cubic", "dm_boost_u8_to_planar",
+    "dm_leres_stem_im2col_f32",
 ]
 
 
@@ -164,6 +167,21 @@ def _bind_optional(L):
         L.dm_subsample2_nhwc_f16.argtypes = [vp, i32, i32, i32, i32, vp, vp]
         L.dm_add_f16.argtypes = [vp, vp, vp, c.c_longlong, vp]
         L.dm_resize_f32_ld.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
+    if hasattr(L, "dm_unet_first_cols"):
+        ll = c.c_longlong
+        L.dm_unet_first_cols.argtypes = [vp, i32, i32, vp, i32, vp]
+        L.dm_unet_down_cols.argtypes = [vp, i32, i32, i32, vp, i32, vp]
+        L.dm_unet_up_cols.argtypes = [vp, i32, vp, i32, i32, i32, vp, i32, vp]
+        L.dm_unet_interleave.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+        L.dm_unet_final.argtypes = [vp, i32, i32, i32, f32, vp, vp]
+        L.dm_boost_minmax.argtypes = [vp, ll, vp, vp]
+        L.dm_boost_merge_input.argtypes = [vp, vp, ll, vp, vp, vp, vp]
+        L.dm_boost_post.argtypes = [vp, ll, vp, i32, vp, vp]
+        L.dm_boost_fit_sums.argtypes = [vp, vp, ll, vp, vp]
+        L.dm_boost_blend.argtypes = [vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp]
+        L.dm_boost_resize_cubic.argtypes = [vp, i32, ll, i32, i32, vp, i32, ll, i32, i32, i32, vp]
+        L.dm_boost_u8_to_planar.argtypes = [vp, i32, i32, vp, vp]
+        L.dm_leres_stem_im2col_f32.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, c.POINTER(c.c_float), c.POINTER(c.c_float), vp, vp]
     if hasattr(L, "dm_zoe_clb_final"):
         L.dm_zoe_preprocess_patchify.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
         L.dm_layernorm_post_f16.argtypes = [vp, c.c_longlong, i32, vp, vp, f32, vp, vp]

@@ -659,9 +659,21 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
         }
         for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 8); mbar_init(&p_full[g], 8); mbar_init(&pv_full[g], 1); }
         fence_barrier_init();
+        // Q and the first two K/V stages need nothing from the rest of the prologue: their loads fly while the CTA fills its bias table
+        mbar_arrive_expect_tx(q_full, b_active ? 2 * AT_Q_BYTES : AT_Q_BYTES);
+        tma_load_2d(sQ, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0);
+        if (b_active) tma_load_2d(sQ + AT_Q_BYTES, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0 + AT_BQ);
+        for (int j = 0; j < min(2, num_kv); ++j) {
+            const int key0 = (ALIGNED && j == num_main) ? 0 : tok0 + j * AT_BKV;
+            mbar_arrive_expect_tx(&k_full[j], AT_KV_BYTES);
+            tma_load_2d(sK + j * AT_KV_BYTES, &tmQKV, &k_full[j], p.C + h * AT_D, row_base + key0);
+            mbar_arrive_expect_tx(&v_full[j], AT_KV_BYTES);
+            tma_load_2d(sV + j * AT_KV_BYTES, &tmQKV, &v_full[j], 2 * p.C + h * AT_D, row_base + key0);
+        }
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
-    for (int i = threadIdx.x; i < A2_ONES_BYTES / 4; i += A4_THREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3c003c00u;
+    if (!PTMEM)
+        for (int i = threadIdx.x; i < A2_ONES_BYTES / 4; i += A4_THREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3c003c00u;
     if (BIAS_MODE >= 2) {
         const float *tab = pp.rel_table + (size_t)h * pp.nrd;
         if (ALIGNED) {
@@ -698,10 +710,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == 0 && lane == 0) {
-            mbar_arrive_expect_tx(q_full, b_active ? 2 * AT_Q_BYTES : AT_Q_BYTES);
-            tma_load_2d(sQ, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0);
-            if (b_active) tma_load_2d(sQ + AT_Q_BYTES, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0 + AT_BQ);
-            for (int j = 0; j < num_kv; ++j) {
+            for (int j = 2; j < num_kv; ++j) {                 // stages 0 and 1 were issued in the prologue
                 const int s = j & 1;
                 const uint32_t ph = ((j >> 1) & 1) ^ 1;
                 const int key0 = (ALIGNED && j == num_main) ? 0 : tok0 + j * AT_BKV;
@@ -830,7 +839,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
             if (lane == 0) mbar_arrive(&s_free[g]);                     // S(j) is in registers: the tensor core may overwrite it
 
             // ---- u = s * scale + bias - m_run, row maximum ---------------------------------------------------------
-            float mx = -INFINITY;
+            float mxv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four independent chains (one FMNMX3 chain of 32 is ~150 cycles)
             const float neg_m = -m_run;
             const uint64_t negm2 = pack2(neg_m, neg_m);
             uint32_t koff4[2] = {0u, 0u};                         // mode 3: the four 16-key chunk offsets of this thread's 64 columns
@@ -881,7 +890,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                     float t0, t1;
                     unpack2(fma2(pack2(__uint_as_float(rc[i]), __uint_as_float(rc[i + 1])), scale2, b2[i >> 1]), t0, t1);
                     if (PARTIAL) { t0 = (c0 + i < nvalid) ? t0 : -INFINITY; t1 = (c0 + i + 1 < nvalid) ? t1 : -INFINITY; }
-                    mx = max3(mx, t0, t1);
+                    mxv[(i >> 1) & 3] = max3(mxv[(i >> 1) & 3], t0, t1);
                     rc[i] = __float_as_uint(t0); rc[i + 1] = __float_as_uint(t1);
                 }
             };
@@ -899,7 +908,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                     }
                 }
             }
-            mx = pair_max(mx);                                   // exact maximum of the row's 128 scores, relative to m_run
+            float mx = pair_max(fmaxf(fmaxf(mxv[0], mxv[1]), fmaxf(mxv[2], mxv[3])));   // exact maximum of the row's 128 scores, relative to m_run
             // tile 0 fixes the reference point; later tiles move it only when a score exceeds it by 2^8 (lazy rescale)
             const bool need = (j == 0) || (mx > 8.0f);
             const bool any_need = __any_sync(0xffffffffu, need);
@@ -936,7 +945,7 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
             if (token) { if (g == 0) asm volatile("bar.sync 9, 512;" ::: "memory"); else asm volatile("bar.sync 10, 512;" ::: "memory"); }
             auto emit = [&](int c) {
                 uint32_t packed[8];
-                float ls0 = 0.f, ls1 = 0.f;
+                uint64_t ls2 = pack2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     float e0, e1;
@@ -960,11 +969,13 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
                         e0 = ex2_approx(__uint_as_float(r[c * 16 + i]));
                         e1 = ex2_approx(__uint_as_float(r[c * 16 + i + 1]));
                     }
-                    if (PTMEM) { ls0 += e0; ls1 += e1; }
+                    if (PTMEM) ls2 = add2(ls2, pack2(e0, e1));
                     const __half2 h2 = __floats2half2_rn(e0, e1);
                     packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
                 }
                 if (PTMEM) {
+                    float ls0, ls1;
+                    unpack2(ls2, ls0, ls1);
                     l_run += ls0 + ls1;
                     tmem_st_32x8(tmem_P + c * 8, packed);
                 } else {

@@ -27,7 +27,7 @@ UNITS = [
     ("normalmap.cu", ["-fmad=false"]),
     ("stereo.cu", ["-fmad=false"]),
 ]
-for _extra in ("vit_kernels.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "zoe_kernels.cu", "leres_kernels.cu", "model.cu"):
+for _extra in ("vit_kernels.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "zoe_kernels.cu", "leres_kernels.cu", "boost_kernels.cu", "model.cu"):
     if os.path.exists(os.path.join(HERE, _extra)):
         UNITS.append((_extra, []))
 

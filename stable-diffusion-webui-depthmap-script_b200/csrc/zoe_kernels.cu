@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const __half *__re
     }
     __syncthreads();
     float *pw = sp + (size_t)warp * S;
-    for (int t = warp; t < S; t += 8) {
+    const int rows_per = (S + gridDim.z - 1) / gridDim.z, t_beg = blockIdx.z * rows_per, t_end = min(S, t_beg + rows_per);
+    for (int t = t_beg + warp; t < t_end; t += 8) {
         const float qd = __half2float(base[(size_t)t * 3 * E + lane]) * scale;
         float mx = -INFINITY;
         for (int j0 = 0; j0 < S; j0 += 32) {                 // uniform trip count: the shuffles need every lane
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(256) attractor_kernel(const float *__restrict_
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const float dx = __shfl_sync(0xffffffffu, a_mine, i) - b;
-        delta += dx / (1.f + 300.f * (dx * dx));
+        delta += __fdividef(dx, 1.f + 300.f * (dx * dx));      // 2 ulp; the head's bar is a tolerance, and this is 16 divisions per thread
     }
     if (ok) bout[((size_t)(f * H + y) * W + x) * 64 + k] = b + delta / 16.f;
 }
@@ -252,70 +253,90 @@ __device__ __forceinline__ float log_binom_f(float n, float k) {   // dist_layer
     return n * logf(n) - k * logf(k) - (n - k) * logf(n - k + 1e-7f);
 }
 
-__global__ void __launch_bounds__(256) clb_final_kernel(ClbParams p) {
+// One THREAD per output pixel (the first version spent a warp per pixel: ~900 warp-instructions per pixel in shuffles, reductions
+// and scalar work replicated 32 times; this form needs ~110).  The weights sit in shared memory and are read as broadcasts; a
+// thread's loads are whole contiguous vectors (64 B of out_conv, 160 B per neighbour of ze, 256 B per neighbour of the bin centres)
+// and neighbouring threads share their bilinear neighbours in L1.
+__global__ void __launch_bounds__(128) clb_final_kernel(ClbParams p) {
     __shared__ float s_wo[32 * 40], s_b0[40], s_w2[4 * 40], s_b2[4], s_lb[64];
     const int f = blockIdx.z;
     const int head = route_of(p.logits, p.lld, f);
-    for (int i = threadIdx.x; i < 32 * 40; i += 256) s_wo[i] = p.wo[head * 32 * 40 + i];
-    for (int i = threadIdx.x; i < 4 * 40; i += 256) s_w2[i] = p.w2[head * 4 * 40 + i];
+    for (int i = threadIdx.x; i < 32 * 40; i += 128) s_wo[i] = p.wo[head * 32 * 40 + i];
+    for (int i = threadIdx.x; i < 4 * 40; i += 128) s_w2[i] = p.w2[head * 4 * 40 + i];
     if (threadIdx.x < 40) s_b0[threadIdx.x] = p.b0[head * 40 + threadIdx.x];
     if (threadIdx.x < 4) s_b2[threadIdx.x] = p.b2[head * 4 + threadIdx.x];
     if (threadIdx.x < 64) s_lb[threadIdx.x] = log_binom_f(63.f, (float)threadIdx.x);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int y = blockIdx.y;
-    const float fy = p.sy * (float)y;
-    const int y0 = min((int)fy, p.h3 - 1), y1 = min(y0 + 1, p.h3 - 1);
-    const float ly = fy - (float)y0, hy = 1.f - ly;
-    const int x_end = min(p.nw, (int)(blockIdx.x + 1) * 64);
-    for (int x = blockIdx.x * 64 + warp; x < x_end; x += 8) {            // one warp per output pixel
-        const float fx = p.sx * (float)x;
-        const int x0 = min((int)fx, p.w3 - 1), x1 = min(x0 + 1, p.w3 - 1);
-        const float lx = fx - (float)x0, hx = 1.f - lx;
-        const size_t i00 = ((size_t)f * p.h3 + y0) * p.w3 + x0, i01 = ((size_t)f * p.h3 + y0) * p.w3 + x1;
-        const size_t i10 = ((size_t)f * p.h3 + y1) * p.w3 + x0, i11 = ((size_t)f * p.h3 + y1) * p.w3 + x1;
-        const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
-        auto bil = [&](const float *base, int ld, int col) {
-            return hy * (hx * base[i00 * ld + col] + lx * base[i01 * ld + col]) + ly * (hx * base[i10 * ld + col] + lx * base[i11 * ld + col]);
-        };
-        (void)w00; (void)w01; (void)w10; (void)w11;
-        // pre-activation of mlp.0: lane owns output k = lane and (lane < 8) k = lane + 32
-        const float o_mine = __half2float(p.o32[(((size_t)f * p.nh + y) * p.nw + x) * p.ldo + lane]);
-        float pre0 = s_b0[lane] + bil(p.ze, p.ldz, head * 64 + lane);
-        float pre1 = lane < 8 ? s_b0[32 + lane] + bil(p.ze, p.ldz, head * 64 + 32 + lane) : 0.f;
+    const int y = blockIdx.y, x = blockIdx.x * 128 + threadIdx.x;
+    if (x >= p.nw) return;
+    const float fy = p.sy * (float)y, fx = p.sx * (float)x;
+    const int y0 = min((int)fy, p.h3 - 1), y1 = min(y0 + 1, p.h3 - 1), x0 = min((int)fx, p.w3 - 1), x1 = min(x0 + 1, p.w3 - 1);
+    const float ly = fy - (float)y0, hy = 1.f - ly, lx = fx - (float)x0, hx = 1.f - lx;
+    const size_t i00 = ((size_t)f * p.h3 + y0) * p.w3 + x0, i01 = ((size_t)f * p.h3 + y0) * p.w3 + x1;
+    const size_t i10 = ((size_t)f * p.h3 + y1) * p.w3 + x0, i11 = ((size_t)f * p.h3 + y1) * p.w3 + x1;
+    // pre-activation of mlp.0 = b0 + W_o . out_conv + bilinear(W_e . b_emb)
+    float pre[40];
+    {
+        const float4 *z00 = reinterpret_cast<const float4 *>(p.ze + i00 * p.ldz + head * 64), *z01 = reinterpret_cast<const float4 *>(p.ze + i01 * p.ldz + head * 64);
+        const float4 *z10 = reinterpret_cast<const float4 *>(p.ze + i10 * p.ldz + head * 64), *z11 = reinterpret_cast<const float4 *>(p.ze + i11 * p.ldz + head * 64);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float oc = __shfl_sync(0xffffffffu, o_mine, c);
-            pre0 = fmaf(s_wo[c * 40 + lane], oc, pre0);
-            if (lane < 8) pre1 = fmaf(s_wo[c * 40 + 32 + lane], oc, pre1);
+        for (int k = 0; k < 10; ++k) {
+            const float4 a = __ldg(z00 + k), b = __ldg(z01 + k), c = __ldg(z10 + k), d = __ldg(z11 + k);
+            pre[4 * k + 0] = s_b0[4 * k + 0] + (hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x));
+            pre[4 * k + 1] = s_b0[4 * k + 1] + (hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y));
+            pre[4 * k + 2] = s_b0[4 * k + 2] + (hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z));
+            pre[4 * k + 3] = s_b0[4 * k + 3] + (hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w));
         }
-        const float g0 = 0.5f * pre0 * (1.f + erff(pre0 * 0.70710678118654752f));                 // nn.GELU (erf form)
-        const float g1 = lane < 8 ? 0.5f * pre1 * (1.f + erff(pre1 * 0.70710678118654752f)) : 0.f;
-        float pt[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float v = s_w2[j * 40 + lane] * g0 + (lane < 8 ? s_w2[j * 40 + 32 + lane] * g1 : 0.f);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            pt[j] = softplus_f(v + s_b2[j]);
-        }
-        const float pa = pt[0] + 1e-4f, pb = pt[1] + 1e-4f, ta = pt[2] + 1e-4f, tb = pt[3] + 1e-4f;
-        const float prob = pa / (pa + pb);
-        const float temp = (p.max_temp - p.min_temp) * (ta / (ta + tb)) + p.min_temp;
-        const float lp = logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
-        // softmax over the 64 bins of y_k / temp, then the expectation of the bin centres; lane owns bins lane and lane + 32
-        const float ya = (s_lb[lane] + (float)lane * lp + (float)(63 - lane) * lq) / temp;
-        const float yb = (s_lb[lane + 32] + (float)(lane + 32) * lp + (float)(31 - lane) * lq) / temp;
-        float mx = fmaxf(ya, yb);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        const float ea = expf(ya - mx), eb = expf(yb - mx);
-        float den = ea + eb;
-        float num = ea * bil(p.bc, 64, lane) + eb * bil(p.bc, 64, lane + 32);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { den += __shfl_xor_sync(0xffffffffu, den, o); num += __shfl_xor_sync(0xffffffffu, num, o); }
-        if (lane == 0) p.out[((size_t)f * p.nh + y) * p.nw + x] = num / den;
     }
+    {
+        const uint4 *op = reinterpret_cast<const uint4 *>(p.o32 + (((size_t)f * p.nh + y) * p.nw + x) * p.ldo);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 u = __ldg(op + q);
+            const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 o2 = __half22float2(h2[e]);
+                const float *w0 = s_wo + (q * 8 + 2 * e) * 40, *w1 = w0 + 40;
+#pragma unroll
+                for (int k = 0; k < 40; ++k) pre[k] = fmaf(w1[k], o2.y, fmaf(w0[k], o2.x, pre[k]));
+            }
+        }
+    }
+    float pt[4] = {s_b2[0], s_b2[1], s_b2[2], s_b2[3]};
+#pragma unroll
+    for (int k = 0; k < 40; ++k) {
+        const float g = 0.5f * pre[k] * (1.f + erff(pre[k] * 0.70710678118654752f));                 // nn.GELU (erf form)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pt[j] = fmaf(s_w2[j * 40 + k], g, pt[j]);
+    }
+    const float pa = softplus_f(pt[0]) + 1e-4f, pb = softplus_f(pt[1]) + 1e-4f, ta = softplus_f(pt[2]) + 1e-4f, tb = softplus_f(pt[3]) + 1e-4f;
+    const float prob = pa / (pa + pb);
+    const float temp = (p.max_temp - p.min_temp) * (ta / (ta + tb)) + p.min_temp;
+    const float lp = logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
+    // softmax over the 64 bins of y_k / temp and the expectation of the (bilinearly up-sampled) bin centres; y_k is concave in k,
+    // its maximum is found in a first pass without touching memory
+    const float inv_t = 1.f / temp;
+    float mx = -INFINITY;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) mx = fmaxf(mx, (s_lb[k] + (float)k * lp + (float)(63 - k) * lq) * inv_t);
+    const float4 *c00 = reinterpret_cast<const float4 *>(p.bc + i00 * 64), *c01 = reinterpret_cast<const float4 *>(p.bc + i01 * 64);
+    const float4 *c10 = reinterpret_cast<const float4 *>(p.bc + i10 * 64), *c11 = reinterpret_cast<const float4 *>(p.bc + i11 * 64);
+    float den = 0.f, num = 0.f;
+#pragma unroll 4
+    for (int k4 = 0; k4 < 16; ++k4) {
+        const float4 a = __ldg(c00 + k4), b = __ldg(c01 + k4), c = __ldg(c10 + k4), d = __ldg(c11 + k4);
+        const float bcv[4] = {hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x), hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y),
+                              hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z), hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = 4 * k4 + e;
+            const float ek = expf((s_lb[k] + (float)k * lp + (float)(63 - k) * lq) * inv_t - mx);
+            den += ek;
+            num = fmaf(ek, bcv[e], num);
+        }
+    }
+    p.out[((size_t)f * p.nh + y) * p.nw + x] = num / den;
 }
 
 // out[b, y, x] = 0.5 * (up(d[2b])[y + pad_h, x + pad_w] + up(d[2b+1])[y + pad_h, Wp - 1 - (x + pad_w)]), up = bicubic
@@ -391,7 +412,7 @@ DM_EXPORT int dm_attention_small_f16(const void *qkv, int F, int S, int heads, f
         if (!configured.test_and_set())
             DM_CUDA_CHECK(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    attention_small_kernel<<<dim3(F, heads), 256, smem, (cudaStream_t)stream_>>>((const __half *)qkv, S, heads * RA_HD, scale, (__half *)out);
+    attention_small_kernel<<<dim3(F, heads, 4), 256, smem, (cudaStream_t)stream_>>>((const __half *)qkv, S, heads * RA_HD, scale, (__half *)out);   // 4 query-row blocks per (forward, head)
     DM_LAUNCH_CHECK("attention_small_kernel");
     return DM_OK;
 }
@@ -446,7 +467,8 @@ DM_EXPORT int dm_zoe_clb_final(const void *o32, int ldo, const float *ze, int ld
     p.sy = nh > 1 ? (float)(h3 - 1) / (float)(nh - 1) : 0.f;
     p.sx = nw > 1 ? (float)(w3 - 1) / (float)(nw - 1) : 0.f;
     p.min_temp = min_temp; p.max_temp = max_temp; p.out = out;
-    clb_final_kernel<<<dim3((unsigned)((nw + 63) / 64), (unsigned)nh, (unsigned)F), 256, 0, (cudaStream_t)stream_>>>(p);
+    if (ldo % 8 || ldz % 4) { set_error("dm_zoe_clb_final: ldo must be a multiple of 8 and ldz of 4"); return DM_E_INVALID; }
+    clb_final_kernel<<<dim3((unsigned)((nw + 127) / 128), (unsigned)nh, (unsigned)F), 128, 0, (cudaStream_t)stream_>>>(p);
     DM_LAUNCH_CHECK("clb_final_kernel");
     return DM_OK;
 }

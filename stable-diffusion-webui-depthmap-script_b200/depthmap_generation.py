@@ -1063,8 +1063,8 @@ class ZoeDepthNKEngine(DptBeitEngine):
         z['clb'] = (we, wo.contiguous(), b0.contiguous(), w2c.contiguous(), b2c.contiguous())
         # out_conv with 64 output channels (32 real + 32 zero) so the stored activation is a valid GEMM-friendly NHWC tensor
         h = 'depth_head.'
-        z['oc2_w64'] = _conv_w(self._oc2_weight.to(dev), self.F2p, 64)
-        z['oc2_b64'] = _pad_vec(self._oc2_bias.to(dev), 64)
+        z['oc2_w'] = _conv_w(self._oc2_weight.to(dev), self.F2p, 32)
+        z['oc2_b'] = self._oc2_bias.to(dev).float().contiguous()
         self.z = z
         self._pe_cache = {}
 
@@ -1107,7 +1107,7 @@ class ZoeDepthNKEngine(DptBeitEngine):
         zb['A'] = [f32(F * h * w, 64) for h, w in levels]
         zb['bnew'] = [f32(F * h * w, 64) for h, w in levels]
         zb['ze'] = f32(F * levels[3][0] * levels[3][1], 128)
-        zb['o32'] = h16(F, nh, nw, 64)
+        zb['o32'] = h16(F, nh, nw, 32)
         zb['d'] = f32(F, nh, nw)
         self._zbufs, self._zbuf_key = zb, key
         return zb
@@ -1137,7 +1137,7 @@ class ZoeDepthNKEngine(DptBeitEngine):
         t = b['up_sizes'][3]
         ops.conv3x3(b['path'][3], F, t[0], t[1], Fp, self.w['oc1_w'], self.F2p, bias=self.w['oc1_b'], C=b['oc1'])
         ops.resize_nhwc(b['oc1'], F, t[0], t[1], self.F2p, b['oc1u'], nh, nw)
-        ops.conv3x3(b['oc1u'], F, nh, nw, self.F2p, z['oc2_w64'], 64, act=A_.ACT_RELU, bias=z['oc2_b64'], C=zb['o32'])
+        ops.conv3x3(b['oc1u'], F, nh, nw, self.F2p, z['oc2_w'], 32, act=A_.ACT_RELU, bias=z['oc2_b'], C=zb['o32'])
         n0, S = zb['n0'], zb['S']
         s3 = b['sizes'][3]
 
@@ -1196,7 +1196,7 @@ class ZoeDepthNKEngine(DptBeitEngine):
         # ---- conditional log-binomial + expectation (:216-236), then un-pad / un-flip / average (depth_model.py:88-129) ----
         we, wo, b0, w2c, b2c = z['clb']
         ops.gemm(zb['bemb'][3], 128, we, 128, F * hp * wp, 128, 128, epi=E_.EPI_STORE_F32, X=zb['ze'], ldx=128)
-        _lib.check(L.dm_zoe_clb_final(zb['o32'].data_ptr(), 64, zb['ze'].data_ptr(), 128, bprev.data_ptr(), lg.data_ptr(), 32, wo.data_ptr(), b0.data_ptr(),
+        _lib.check(L.dm_zoe_clb_final(zb['o32'].data_ptr(), 32, zb['ze'].data_ptr(), 128, bprev.data_ptr(), lg.data_ptr(), 32, wo.data_ptr(), b0.data_ptr(),
                                       w2c.data_ptr(), b2c.data_ptr(), F, nh, nw, hp, wp, ZOE_CONFIG['min_temp'], ZOE_CONFIG['max_temp'],
                                       zb['d'].data_ptr(), st()), "dm_zoe_clb_final")
         out = torch.empty(B, H, W, dtype=torch.float32, device=self.device)
