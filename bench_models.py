@@ -380,4 +380,139 @@ class Dav2StereoSmall(Dav2Stereo):
     heads, C = 6, 384
 
 
-MODEL_WORKLOADS = {"depth_beit512": DepthBeit512, "dav2_stereo": Dav2Stereo, "dav2s_stereo": Dav2StereoSmall, "zoedepth_nk768": ZoeAnaglyph}
+class BoostRes101:
+    """BASELINE.json configs[4]: BoostingMonocularDepth multi-resolution merge (LeReS res101 base + pix2pix merge net) on a 2048x2048
+    synthetic image.  One image per step; with N GPUs the image's patches are dealt to the ranks (patch-parallel, one all-gather of the
+    fitted patches, every rank replays the blend): STRONG scaling.  `value` = images/s with the image resident and the host control plane
+    (R_x search + patch selection, a function of the RGB image only) computed once outside the timed region; `e2e` = the public call
+    ModelHolder.get_raw_prediction(PIL image) including that control plane, the H2D of the image and the D2H of the depth map."""
+    name = "boost_res101_2048"
+    H = W = 2048
+    B = 1
+    dtype = "fp16 (LeReS operands) / split fp16 = fp32-class (merge net), fp32 accumulate"
+    RMAX = 1600                                   # the reference's default boost_rmax (src/backbone.py:36-49)
+
+    def __init__(self, dev, rank):
+        from bench import make_images
+        from depthmap_b200.depthmap_generation import ModelHolder
+        from oracle import synth_weights
+        self.dev = dev
+        lsd = synth_weights.make_leres_state_dict(seed=2)
+        psd = synth_weights.make_pix2pix_state_dict(seed=1)
+        self.holder = ModelHolder()
+        self.holder.weights_provider = lambda t: psd if t == "pix2pix" else lsd
+        self.holder.update_settings(boost_rmax=self.RMAX)
+        self.holder.ensure_models(0, dev, True)
+        self.pipe = self.holder.pix2pix_model
+        rgb, _ = make_images(1, self.H, self.W, 0)            # every rank works on the SAME image
+        self.rgb = rgb[0]
+
+    def config(self):
+        return {"workload": "BOOST: LeReS res101 double estimation + pix2pix merge net, 2048x2048 -> 2048x2048 fp32 depth", "images_per_step": 1,
+                "height": self.H, "width": self.W, "boost_rmax": self.RMAX, "weights": "seeded synthetic, res101.pth / latest_net_G.pth layouts",
+                "l2_policy": "per-image activations (several GB) far exceed the 126 MB L2"}
+
+    def measure(self, args, world, dev, rank, local_rank, peaks, steps, with_cpu_baseline, ClockSampler):
+        import torch
+        import torch.distributed as dist
+        from PIL import Image
+        from depthmap_b200 import boost
+        import cv2
+        group = dist.group.WORLD if world > 1 else None
+        info = {}
+        self.pipe.run(self.rgb, self.RMAX, group=group, info=info)           # warm-up 1 (allocations), also yields the plan
+        plan = {k: info[k] for k in ("rf", "whole", "patch_scale", "factor", "target", "work", "rects", "scaled_rects")}
+        for _ in range(max(args.warmup - 1, 1)):
+            self.pipe.run(self.rgb, self.RMAX, group=group, precomputed=plan, to_host=False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n0 = self.pipe.launches + self.pipe.depth.ops.launches + self.pipe.merge.ops.launches
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.pipe.run(self.rgb, self.RMAX, group=group, precomputed=plan, to_host=False)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        launches = self.pipe.launches + self.pipe.depth.ops.launches + self.pipe.merge.ops.launches - n0
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / steps
+        # e2e through the public API (rank 0's wall clock around the call; the call ends with a D2H copy, i.e. it is synchronous)
+        pil = Image.fromarray(self.rgb)
+        if world == 1:
+            self.holder.get_raw_prediction(pil, 448, 448)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                pred, _ = self.holder.get_raw_prediction(pil, 448, 448)
+            ms_e2e = (time.perf_counter() - t0) / steps * 1e3
+        else:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                self.pipe.run(self.rgb, self.RMAX, group=group)
+            ms_e2e = (time.perf_counter() - t0) / steps * 1e3
+        if rank != 0:
+            return None
+        n_patches = len(plan["rects"])
+        # algorithmic FLOPs (SURVEY 8d, FlopCounterMode on the reference modules): LeReS 290.0 GFLOP at 448^2 scaling with the pixel count,
+        # merge net 191.1 GFLOP per 1024^2 call; whole image: 2 LeReS + 1 merge; per patch: 2 LeReS (448, 896) + 2 merges
+        leres = lambda s: 290.0e9 * (s / 448.0) ** 2
+        flops = leres(448) + leres(plan["whole"]) + 191.1e9 + n_patches * (leres(448) + leres(896) + 2 * 191.1e9)
+        line = {"metric": "images/sec", "value": 1000.0 / ms_step, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
+                "config": dict(self.config(), patches=n_patches, whole_size=plan["whole"], target=list(plan["target"]),
+                               parallelism=("patch-parallel over %d ranks, one all-gather" % world) if world > 1 else "single GPU, patches one by one"),
+                "clocks": clocks, "gpu_launches": launches, "launch_mode": "eager (B = 1 forwards, host-launch bound)",
+                "e2e": {"value": 1000.0 / ms_e2e, "unit": "images/s", "h2d_bytes_per_step": self.H * self.W * 3, "d2h_bytes_per_step": self.H * self.W * 4,
+                        "ms_per_step": ms_e2e, "api": "ModelHolder.get_raw_prediction(PIL image) with boost: host control plane (cv2 Sobel / integral image on the "
+                                                      "3136-px work image) + H2D + every network pass + D2H, wall clock"},
+                "roofline": {"bound": "tensor", "kernel": "whole step (no single dominant kernel: ~%d launches per image, B = 1)" % (launches // max(steps, 1)),
+                             "achieved": flops / (ms_step * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": flops / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"],
+                             "algorithmic_flops_per_launch": flops,
+                             "note": "algorithmic FLOPs of the fp32 reference networks; the merge net spends 3x that on the tensor core (split operands)"}}
+        if world == 1 and with_cpu_baseline:
+            import oracle
+            from bench import host_threads, pick_torch_threads
+            oracle.build()
+            cores = pick_torch_threads(host_threads())
+            n, dt, what = self.cpu_sample(cores)
+            line["cpu_baseline"] = {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port", "sample": what}
+        return line
+
+    def cpu_sample(self, nthreads):
+        """Bounded sample of the reference CPU path: ONE patch's network work (LeReS at 448 and 896 + two merge-net calls, fp32 torch through
+        oracle/), scaled to the image by the patch count + the whole-image prefix at the same per-FLOP rate."""
+        import torch
+        from oracle import leres, pix2pix as op2p, synth_weights
+        torch.set_num_threads(nthreads)
+        lsd = synth_weights.make_leres_state_dict(seed=2)
+        psd = synth_weights.make_pix2pix_state_dict(seed=1)
+        crop = (self.rgb[:900, :900].astype(np.float64) / 255.0)[:, :, ::-1]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            a = leres.estimateleres(crop, lsd, 448, 448)
+            b = leres.estimateleres(crop, lsd, 896, 896)
+            import cv2
+            a = cv2.resize(a, (1024, 1024), interpolation=cv2.INTER_CUBIC)
+            b = cv2.resize(b, (1024, 1024), interpolation=cv2.INTER_CUBIC)
+            m = op2p.unet(psd, op2p.merge_input(a, b))[0, 0].numpy()
+            op2p.unet(psd, op2p.merge_input(a, m))
+        dt = time.perf_counter() - t0
+        per_patch_flops = 290.0e9 * (1 + 4) + 2 * 191.1e9
+        info = {}
+        from depthmap_b200 import boost
+        import cv2
+        p = boost.plan(cv2.cvtColor(self.rgb, cv2.COLOR_BGR2RGB) / 255.0, 0, self.RMAX)
+        total = 290.0e9 * (1 + (p["whole"] / 448.0) ** 2) + 191.1e9 + len(p["rects"]) * per_patch_flops
+        est = dt * total / per_patch_flops
+        return 1, est, (f"one patch's double estimation + merge measured ({dt:.1f} s, fp32 torch CPU through oracle/), extrapolated by FLOPs to the image's "
+                        f"{len(p['rects'])} patches + whole-image prefix = {est:.0f} s per image")
+
+
+MODEL_WORKLOADS = {"boost_res101_2048": BoostRes101, "depth_beit512": DepthBeit512, "dav2_stereo": Dav2Stereo, "dav2s_stereo": Dav2StereoSmall, "zoedepth_nk768": ZoeAnaglyph}

@@ -254,3 +254,29 @@ def make_leres_state_dict(seed=0, dtype=torch.float32):
     bn(D + 'outconv.adapt_conv.1', 128)
     conv(D + 'outconv.adapt_conv.3', 1, 128, 3, bias=True)
     return sd
+
+
+def make_pix2pix_state_dict(seed=0, dtype=torch.float32):
+    """Seeded synthetic state_dict with the keys and shapes of the BOOST merge generator, pix2pix `define_G(2, 1, 64, 'unet_1024',
+    'none')` (pix2pix/models/networks.py:444-543): 10 nested UnetSkipConnectionBlocks, only the outermost ConvTranspose has a bias.
+    Gain 1.3 / sqrt(fan_in) (fan-in of a stride-2 4x4 transposed conv = 4 taps x input channels) keeps a signal through the 20
+    un-normalised layers without saturating the final tanh: output std ~0.4, input sensitivity ~6 (max) / ~1 (rms)."""
+    g = torch.Generator().manual_seed(seed)
+    ch = [(2, 64), (64, 128), (128, 256), (256, 512)] + [(512, 512)] * 6
+    sd = {}
+    prefix = "model."
+    for d, (cin, cout) in enumerate(ch):
+        if d == 0:
+            kd, ku, child = prefix + "model.0.weight", prefix + "model.3.weight", prefix + "model.1."
+        elif d == 9:
+            kd, ku, child = prefix + "model.1.weight", prefix + "model.3.weight", None
+        else:
+            kd, ku, child = prefix + "model.1.weight", prefix + "model.5.weight", prefix + "model.3."
+        sd[kd] = (torch.randn(cout, cin, 4, 4, generator=g) * (1.3 / (cin * 16) ** 0.5)).to(dtype)
+        up_in = cout if d == 9 else 2 * cout
+        up_out = 1 if d == 0 else cin
+        sd[ku] = (torch.randn(up_in, up_out, 4, 4, generator=g) * (1.3 / (up_in * 4) ** 0.5)).to(dtype)
+        if d == 0:
+            sd[prefix + "model.3.bias"] = (0.05 * torch.randn(1, generator=g)).to(dtype)
+        prefix = child
+    return sd

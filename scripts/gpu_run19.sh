@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_boost_gpu.py -m gpu -q -s -p no:cacheprovider > gpurun_out/r2_pytest19.log 2>&1; echo "rc=$?" >> gpurun_out/r2_pytest19.log
+grep -E "precision|passed|failed|^FAILED|^ERROR|rc=|Error|error" gpurun_out/r2_pytest19.log | tail -30

@@ -247,8 +247,19 @@ __global__ void __launch_bounds__(256) boost_blend_kernel(const float *__restric
         s_sum[threadIdx.x] = t;
     }
     __syncthreads();
+    // np.polyfit(x, y, 1) as the reference calls it (:911): x and y are float32, so polyfit's rcond is len(x) * eps(float32) = 2^20 * 2^-23
+    // = 0.125 — the SVD least squares on the column-normalised Vandermonde matrix [x / |x|, 1 / sqrt(n)] DROPS the second singular value
+    // whenever sqrt(1 - c) <= 0.125 sqrt(1 + c), c = cos(x, 1) = sum x / (|x| sqrt n): for a merged patch whose spread is below ~25 % of
+    // its mean the "degree-1 fit" is the rank-1 minimum-norm solution, not the regression line (numpy warns "poorly conditioned" and
+    // goes on).  The Gram matrix of two unit columns is [[1, c], [c, 1]]: eigenvectors (1, 1) / sqrt 2 and (1, -1) / sqrt 2, eigenvalues
+    // 1 + c and 1 - c, so the (truncated) pseudo-inverse is closed-form in the five sums.
     const double n = (double)n_fit, sx = s_sum[0], sy = s_sum[1], sxx = s_sum[2], sxy = s_sum[3];
-    const double slope = (n * sxy - sx * sy) / (n * sxx - sx * sx), icpt = (sy - slope * sx) / n;
+    const double nx = sqrt(sxx), nn = sqrt(n);
+    const double c = sx / (nx * nn), b0 = sxy / nx, b1 = sy / nn;
+    const double rcond = n * 1.1920928955078125e-07;
+    double c0 = (b0 + b1) / (2.0 * (1.0 + c)), c1 = c0;
+    if (sqrt(1.0 - c) > rcond * sqrt(1.0 + c)) { const double t = (b0 - b1) / (2.0 * (1.0 - c)); c0 += t; c1 -= t; }
+    const double slope = c0 / nx, icpt = c1 / nn;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= (long long)w * h) return;
     const int x = (int)(idx % w), y = (int)(idx / w);

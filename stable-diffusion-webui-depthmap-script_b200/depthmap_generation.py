@@ -778,13 +778,20 @@ class LeresEngine:
         return t
 
     # ---- forward ---------------------------------------------------------------------------------------------------
-    def forward_batch(self, rgb, net_w, net_h=None, out_hw=None):
-        """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] (what estimateleres returns; invert = True)."""
+    def forward_batch(self, rgb, net_w, net_h=None, out_hw=None, planar=None):
+        """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] (what estimateleres returns; invert = True).
+        planar = (fp32 CUDA [3,Hi,Wi] image in network channel order, (x0, y0, w, h)) instead of `rgb`: estimateleres on a float
+        crop, as BOOST calls it (src/depthmap_generation.py:1053-1056) — one image, result [1, h, w]."""
         import torch
         ops, w, L = self.ops, self.w, self.ops.L
         st = _lib.stream_ptr
         A = _lib
-        B, H, W, _ = rgb.shape
+        if planar is None:
+            B, H, W, _ = rgb.shape
+        else:
+            pl_img, rect = planar
+            pl_hi, pl_wi = int(pl_img.shape[1]), int(pl_img.shape[2])
+            B, H, W = 1, int(rect[3]), int(rect[2])
         net_h = net_h if net_h is not None else net_w
         if net_w % 32 or net_h % 32:
             raise ValueError("LeReS needs a net size that is a multiple of 32")
@@ -793,7 +800,11 @@ class LeresEngine:
         cols = self._buf('stem_cols', (B * h1 * w1, 192))
         m = (ctypes.c_float * 3)(*self.MEAN)
         s = (ctypes.c_float * 3)(*self.STD)
-        _lib.check(L.dm_leres_stem_im2col(rgb.data_ptr(), B, H, W, net_h, net_w, m, s, cols.data_ptr(), st()), "dm_leres_stem_im2col")
+        if planar is None:
+            _lib.check(L.dm_leres_stem_im2col(rgb.data_ptr(), B, H, W, net_h, net_w, m, s, cols.data_ptr(), st()), "dm_leres_stem_im2col")
+        else:
+            _lib.check(L.dm_leres_stem_im2col_f32(pl_img.data_ptr(), pl_hi, pl_wi, rect[0], rect[1], rect[2], rect[3], net_h, net_w, m, s, cols.data_ptr(),
+                                                  st()), "dm_leres_stem_im2col_f32")
         x = self._buf('stem', (B, h1, w1, 64))
         ops.gemm(cols, 192, w['stem'][0], 192, B * h1 * w1, 64, 192, act=A.ACT_RELU, bias=w['stem'][1], C=x, ldc=64)
         h, wd = (h1 + 2 - 3) // 2 + 1, (w1 + 2 - 3) // 2 + 1
@@ -1241,8 +1252,9 @@ class ModelHolder:
         """Ensure that the depth model is loaded (reference: src/depthmap_generation.py:76-301)."""
         import torch
         _lib.require_cuda()
-        if boost:
-            raise NotImplementedError("BOOST is not implemented in depthmap_b200 yet (SURVEY.md §8 row D9)")
+        if boost and model_type != 0:
+            raise NotImplementedError("BOOST is built for the reference's default base network only, LeReS res101 (model type 0); "
+                                      "the other base networks (estimatemidasBoost etc.) are not implemented in depthmap_b200")
         if tiling_mode:
             raise NotImplementedError("tiling_mode (circular conv padding) is not implemented in depthmap_b200 yet")
         if getattr(self, "no_half", False):
@@ -1284,6 +1296,16 @@ class ModelHolder:
                 if "depth_model" in sd:      # src/depthmap_generation.py:113-116: strip_prefix_if_present(checkpoint['depth_model'], "module.")
                     sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd["depth_model"].items()}
             model = LeresEngine(sd, torch.device(device))
+            if boost:      # reference :284-299: the pix2pix merge network ('latest_net_G.pth', netG = unet_1024, norm none)
+                from .boost import BoostPipeline, UnetMergeEngine
+                if self.weights_provider is not None:
+                    psd = self.weights_provider("pix2pix")
+                else:
+                    p2p_path = "./models/pix2pix/latest_net_G.pth"
+                    if not os.path.exists(p2p_path):
+                        raise FileNotFoundError(f"{p2p_path} not found (depthmap_b200 does not download checkpoints)")
+                    psd = torch.load(p2p_path, map_location='cpu')
+                self.pix2pix_model = BoostPipeline(model, UnetMergeEngine(psd, torch.device(device)), torch.device(device), model_type)
         elif model_type == 3:  # dpt_large_384 (MiDaS 3.0)
             if self.weights_provider is not None:
                 sd = self.weights_provider(model_type)
@@ -1371,6 +1393,8 @@ class ModelHolder:
         img = np.asarray(input)
         if img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
             img = np.asarray(input.convert('RGB')) if hasattr(input, 'convert') else img
+        if self.pix2pix_model is not None:       # boost: net_width / net_height are ignored (reference :376-377, :399-401)
+            return self.pix2pix_model.run(img, self.boost_rmax), self.depth_model_type in [0, 7, 8, 9, 10]
         t = torch.from_numpy(np.ascontiguousarray(img)).to(dev).unsqueeze(0)
         pred, invert = self.get_raw_prediction_batch(t, net_width, net_height)
         return pred[0].cpu().numpy(), invert

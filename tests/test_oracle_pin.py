@@ -381,3 +381,13 @@ def test_boost_estimate_equals_reference():
     got = boost.estimateboost(img.copy(), 0, _fake_estimate, _fake_merge, 1600, info=info)
     assert got.shape == want.shape == (300, 420) and len(info["patches"]) >= 2
     assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+
+
+def test_pix2pix_synthetic_state_dict_matches_reference_module():
+    """oracle.synth_weights.make_pix2pix_state_dict loads strictly into the reference generator"""
+    ref_loader.bootstrap()
+    from pix2pix.models import networks
+    from oracle import synth_weights
+    net = networks.define_G(2, 1, 64, 'unet_1024', 'none', False, 'normal', 0.02, [])
+    res = net.load_state_dict(synth_weights.make_pix2pix_state_dict(seed=1), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
