@@ -467,7 +467,7 @@ class BoostRes101:
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
                 "config": dict(self.config(), patches=n_patches, whole_size=plan["whole"], target=list(plan["target"]),
                                parallelism=("patch-parallel over %d ranks, one all-gather" % world) if world > 1 else "single GPU, patches one by one"),
-                "clocks": clocks, "gpu_launches": launches, "launch_mode": "eager (B = 1 forwards, host-launch bound)",
+                "clocks": clocks, "gpu_launches": launches, "launch_mode": "cuda_graph per network (LeReS per net size, merge net); glue kernels eager",
                 "e2e": {"value": 1000.0 / ms_e2e, "unit": "images/s", "h2d_bytes_per_step": self.H * self.W * 3, "d2h_bytes_per_step": self.H * self.W * 4,
                         "ms_per_step": ms_e2e, "api": "ModelHolder.get_raw_prediction(PIL image) with boost: host control plane (cv2 Sobel / integral image on the "
                                                       "3136-px work image) + H2D + every network pass + D2H, wall clock"},

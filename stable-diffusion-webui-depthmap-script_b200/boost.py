@@ -148,6 +148,14 @@ def plan(img_f64, model_type, whole_size_threshold):
 # ---------------------------------------------------------------------------------------------------------------------
 # merge network
 # ---------------------------------------------------------------------------------------------------------------------
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class UnetMergeEngine:
     """pix2pix `unet_1024` generator (2 -> 1 channels, 10 levels, norm 'none'): down = [LeakyReLU(0.2), Conv 4x4/2], up = [ReLU,
     ConvTranspose 4x4/2] with skip concatenation, tanh at the end (pix2pix/models/networks.py:444-543).  Activations stay fp32 NHWC;
@@ -196,6 +204,12 @@ class UnetMergeEngine:
                 self.bias = float(sd[prefix + "model.3.bias"].detach().float().item())
             prefix = child
         self._bufs = {}
+        # every call has the same shapes: after one eager call (allocations) the ~600 launches of a forward are captured into a CUDA
+        # graph and replayed (DEPTHMAP_B200_UNET_GRAPH=0 keeps it eager)
+        import os
+        self._use_graph = os.environ.get("DEPTHMAP_B200_UNET_GRAPH", "1") != "0"
+        self._graph, self._static_in, self._static_out, self._calls = None, None, None, 0
+        self._streams = [torch.cuda.Stream(device=device) for _ in range(8)] if self.split else []
 
     def _operand(self, m):
         """-> (fp16 operand [N, K * copies], fp32 [N] output scale).  Split mode scales the filter bank by a power of two first so
@@ -210,23 +224,42 @@ class UnetMergeEngine:
         lo = (m - hi.float()).half()
         return torch.cat([hi, hi, lo], dim=1).contiguous(), torch.full((m.shape[0],), 2.0 ** -k, dtype=torch.float32, device=m.device)
 
-    def _gemm(self, cols, K, operand, M, N, out):
-        """out[M, N] (fp32) = cols[M, K] @ W^T.  Split mode: depth chunks of `kc`, every chunk accumulated inside the tensor core and
-        added to `out` in fp32 by the epilogue (X += gamma * acc): the tensor core's own fp32 accumulator aligns and truncates each
-        partial sum, a bias that grows with the number of K steps; short chains + a rounding fp32 add keep it at the 1e-6 level."""
-        w, gamma = operand
+    def _gemms(self, jobs):
+        """jobs: [(cols [M, K] fp16, K, operand, M, N, out [M, N] fp32)] — the GEMMs of one layer (one for a convolution, the four parities
+        of a transposed one).  out = cols @ W^T.
+        Split mode cuts the tripled depth into chunks of `kc`: the tensor core's own fp32 accumulator aligns and TRUNCATES partial sums, a
+        bias that grows linearly with the number of K steps (tools/probe_tensor_core.py), so every chunk is accumulated on its own and
+        the chunks are added in a fixed order by a rounding fp32 adder (dm_sum_chunks_f32, which also undoes the filter pre-scale).
+        The chunk GEMMs of a layer are independent (deep levels: a handful of CTAs each, ~20 us of latency): they are issued round-robin
+        on side streams — concurrent branches of the captured graph — and joined before the reduction."""
+        import torch
         if not self.split:
-            self.ops.gemm(cols, K, w, K, M, N, K, epi=_lib.EPI_STORE_F32, X=out, ldx=N)
+            for cols, K, (w, _), M, N, out in jobs:
+                self.ops.gemm(cols, K, w, K, M, N, K, epi=_lib.EPI_STORE_F32, X=out, ldx=N)
             return
-        out.zero_()
-        kc = self.kc or K
-        esz = 2
-        for k0 in range(0, K, kc):
-            kk = min(kc, K - k0)
+        main = torch.cuda.current_stream()
+        launches = []
+        for ji, (cols, K, (w, gamma), M, N, out) in enumerate(jobs):
+            kc = self.kc or K
+            chunks = [(k0, min(kc, K - k0)) for k0 in range(0, K, kc)]
+            ws = self._buf(f"ws{ji}", (len(chunks), M, N), torch.float32)
+            for ci, (k0, kk) in enumerate(chunks):
+                launches.append((cols, K, w, M, N, k0, kk, ws[ci]))
+            jobs[ji] = (ws, len(chunks), M, N, gamma, out)
+        streams = self._streams[:min(len(self._streams), len(launches))] if len(launches) > 1 else []
+        for s_ in streams:
+            s_.wait_stream(main)
+        for li, (cols, K, w, M, N, k0, kk, dst) in enumerate(launches):
             d = _lib.GemmDesc()
-            d.M, d.N, d.K, d.epi, d.act = M, N, kk, _lib.EPI_RESID_F32, _lib.ACT_NONE
-            d.X, d.ldx, d.gamma = out.data_ptr(), N, gamma.data_ptr()
-            _lib.check(self.ops.L.dm_gemm_ex(cols.data_ptr() + k0 * esz, K, w.data_ptr() + k0 * esz, K, ctypes.byref(d), _lib.stream_ptr()), "dm_gemm_ex")
+            d.M, d.N, d.K, d.epi, d.act = M, N, kk, _lib.EPI_STORE_F32, _lib.ACT_NONE
+            d.X, d.ldx = dst.data_ptr(), N
+            with torch.cuda.stream(streams[li % len(streams)]) if streams else _NullCtx():
+                _lib.check(self.ops.L.dm_gemm_ex(cols.data_ptr() + k0 * 2, K, w.data_ptr() + k0 * 2, K, ctypes.byref(d), _lib.stream_ptr()), "dm_gemm_ex")
+            self.ops.launches += 1
+        for s_ in streams:
+            main.wait_stream(s_)
+        for ws, n, M, N, gamma, out in jobs:
+            _lib.check(self.ops.L.dm_sum_chunks_f32(ws.data_ptr(), n, M * N, N, gamma.data_ptr(), out.data_ptr(), _lib.stream_ptr()), "dm_sum_chunks_f32")
             self.ops.launches += 1
 
     def _buf(self, name, shape, dtype):
@@ -240,6 +273,31 @@ class UnetMergeEngine:
 
     def forward(self, x2):
         """x2: fp32 CUDA [1024, 1024, 2] (real_A as NHWC) -> fp32 CUDA [1024, 1024] in (-1, 1)"""
+        import torch
+        if self._graph is not None and x2.shape == self._static_in.shape and not torch.cuda.is_current_stream_capturing():
+            self._static_in.copy_(x2)
+            self._graph.replay()
+            self.ops.launches += self._graph_launches                # the kernels inside the graph still launch
+            return self._static_out.clone()
+        self._calls += 1
+        if self._use_graph and self._calls == 2 and not torch.cuda.is_current_stream_capturing():
+            try:
+                self._static_in = x2.clone()
+                g = torch.cuda.CUDAGraph()
+                n0 = self.ops.launches
+                with torch.cuda.graph(g):
+                    self._static_out = self._forward(self._static_in)
+                self._graph, self._graph_launches = g, self.ops.launches - n0
+                g.replay()
+                return self._static_out.clone()
+            except Exception as e:  # noqa: BLE001 — capture is an optimisation; the eager path below is the same kernels
+                import sys
+                sys.stderr.write(f"[depthmap_b200] merge-net graph capture failed ({e}); running eagerly\n")
+                torch.cuda.synchronize()
+                self._graph, self._use_graph = None, False
+        return self._forward(x2)
+
+    def _forward(self, x2):
         import torch
         L, ops, st, cp = self.ops.L, self.ops, _lib.stream_ptr, self.copies
         S = int(x2.shape[0])
@@ -256,7 +314,7 @@ class UnetMergeEngine:
             else:
                 _lib.check(L.dm_unet_down_cols(h[d - 1].data_ptr(), Hin, Hin, cin, cols.data_ptr(), int(self.split), st()), "dm_unet_down_cols")
             out = self._buf(f"h{d}", (M, cout), torch.float32)
-            self._gemm(cols, K, self.down[d], M, cout, out)
+            self._gemms([(cols, K, self.down[d], M, cout, out)])
             ops.launches += 1
             h.append(out)
         u, cu = None, 0
@@ -271,8 +329,7 @@ class UnetMergeEngine:
             weights, cout = self.up[d]
             N = max(cout, 32)
             tmp = self._buf("tmp", (4, M, N), torch.float32)
-            for par in range(4):
-                self._gemm(cols[par], K, weights[par], M, N, tmp[par])
+            self._gemms([(cols[par], K, weights[par], M, N, tmp[par]) for par in range(4)])
             if d > 0:
                 u = self._buf(f"u{d}", (2 * Hs, 2 * Hs, cout), torch.float32)
                 _lib.check(L.dm_unet_interleave(tmp.data_ptr(), Hs, Hs, N, cout, u.data_ptr(), st()), "dm_unet_interleave")

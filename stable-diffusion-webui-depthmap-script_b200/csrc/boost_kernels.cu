@@ -147,6 +147,20 @@ __global__ void __launch_bounds__(256) unet_final_kernel(const float *__restrict
     out[idx] = tanhf(tmp[((long long)par * H * W + (long long)(oy >> 1) * W + (ox >> 1)) * N] + bias);
 }
 
+// out[i] = gamma[i % N] * (ws[0][i] + ws[1][i] + ...): the K chunks of a split-operand GEMM, added in a FIXED order by a rounding fp32 adder
+__global__ void __launch_bounds__(256) sum_chunks_kernel(const float *__restrict__ ws, int nchunks, long long mn, int N, const float *__restrict__ gamma,
+                                                         float *__restrict__ out) {
+    const long long i4 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i4 >= mn) return;
+    float4 acc = *reinterpret_cast<const float4 *>(ws + i4);
+    for (int c = 1; c < nchunks; ++c) {
+        const float4 v = *reinterpret_cast<const float4 *>(ws + (long long)c * mn + i4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float4 g = *reinterpret_cast<const float4 *>(gamma + (int)(i4 % N));
+    *reinterpret_cast<float4 *>(out + i4) = make_float4(acc.x * g.x, acc.y * g.y, acc.z * g.z, acc.w * g.w);
+}
+
 // ---- reductions ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) boost_minmax_kernel(const float *__restrict__ x, long long n, float *__restrict__ partial) {
     float lo = INFINITY, hi = -INFINITY;
@@ -416,6 +430,14 @@ DM_EXPORT int dm_unet_final(const float *tmp, int H, int W, int N, float bias, f
     if (!tmp || !out) { set_error("dm_unet_final: null argument"); return DM_E_INVALID; }
     unet_final_kernel<<<GRID(4ll * H * W), 256, 0, (cudaStream_t)stream_>>>(tmp, H, W, N, bias, out);
     DM_LAUNCH_CHECK("unet_final_kernel");
+    return DM_OK;
+}
+
+DM_EXPORT int dm_sum_chunks_f32(const float *ws, int nchunks, long long mn, int N, const float *gamma, float *out, void *stream_) {
+    using namespace dm;
+    if (!ws || !gamma || !out || nchunks < 1 || (N % 4) || (mn % N)) { set_error("dm_sum_chunks_f32: bad arguments"); return DM_E_INVALID; }
+    sum_chunks_kernel<<<GRID(mn / 4), 256, 0, (cudaStream_t)stream_>>>(ws, nchunks, mn, N, gamma, out);
+    DM_LAUNCH_CHECK("sum_chunks_kernel");
     return DM_OK;
 }
 

@@ -18,6 +18,7 @@ import ctypes
 import gc
 import math
 import os
+import sys
 
 import numpy as np
 
@@ -695,6 +696,8 @@ class LeresEngine:
         self.device = device
         self.ops = _Ops()
         self._bufs, self._buf_key = {}, None
+        self._graphs, self._graph_calls = {}, {}
+        self._use_graph = os.environ.get("DEPTHMAP_B200_LERES_GRAPH", "1") != "0"
         self._pack(state_dict)
 
     # ---- weights -------------------------------------------------------------------------------------------------------
@@ -771,13 +774,42 @@ class LeresEngine:
     def _buf(self, name, shape, dtype=None):
         import torch
         dtype = dtype or torch.float16
-        t = self._bufs.get(name)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        key = (name, tuple(shape), dtype)          # one set of buffers per net size: BOOST alternates 448 / 896 / whole-image nets, and the
+        t = self._bufs.get(key)                    # captured graphs below need stable addresses
+        if t is None:
             t = torch.empty(*shape, dtype=dtype, device=self.device)
-            self._bufs[name] = t
+            self._bufs[key] = t
         return t
 
     # ---- forward ---------------------------------------------------------------------------------------------------
+    def _network(self, B, net_h, net_w, cols):
+        """stem GEMM .. decoder output [B, net_h, net_w] fp32 (a pooled buffer).  From the second call on at a given (B, net size) the
+        ~500 launches replay from a CUDA graph (DEPTHMAP_B200_LERES_GRAPH=0: eager)."""
+        import torch
+        key = (B, net_h, net_w)
+        capturing = torch.cuda.is_current_stream_capturing()       # inside somebody else's capture: plain launches
+        g = self._graphs.get(key)
+        if g is not None and not capturing:
+            g[0].replay()
+            self.ops.launches += g[2]                                # the kernels inside the graph still launch
+            return g[1]
+        n = self._graph_calls.get(key, 0) + 1
+        self._graph_calls[key] = n
+        if self._use_graph and g is None and n >= 2 and not capturing:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                n0 = self.ops.launches
+                with torch.cuda.graph(graph):
+                    dn = self._network_eager(B, net_h, net_w, cols)
+                self._graphs[key] = (graph, dn, self.ops.launches - n0)
+                graph.replay()
+                return dn
+            except Exception as e:  # noqa: BLE001 — an optimisation only: same kernels eagerly
+                sys.stderr.write(f"[depthmap_b200] LeReS graph capture failed ({e}); running eagerly\n")
+                torch.cuda.synchronize()
+                self._use_graph = False
+        return self._network_eager(B, net_h, net_w, cols)
+
     def forward_batch(self, rgb, net_w, net_h=None, out_hw=None, planar=None):
         """rgb: uint8 CUDA [B,H,W,3] -> float32 CUDA [B,H,W] (what estimateleres returns; invert = True).
         planar = (fp32 CUDA [3,Hi,Wi] image in network channel order, (x0, y0, w, h)) instead of `rgb`: estimateleres on a float
@@ -805,6 +837,23 @@ class LeresEngine:
         else:
             _lib.check(L.dm_leres_stem_im2col_f32(pl_img.data_ptr(), pl_hi, pl_wi, rect[0], rect[1], rect[2], rect[3], net_h, net_w, m, s, cols.data_ptr(),
                                                   st()), "dm_leres_stem_im2col_f32")
+        dn = self._network(B, net_h, net_w, cols)
+        hh, ww = net_h // 2, net_w // 2
+        oh, ow = out_hw if out_hw is not None else (H, W)
+        out = torch.empty(B, oh, ow, dtype=torch.float32, device=self.device)
+        if (oh, ow) == (2 * hh, 2 * ww):
+            out.copy_(dn)                                      # cv2.resize to the same size is a copy
+        else:
+            ops.resize_f32(dn, B, 2 * hh, 2 * ww, out, oh, ow, 1)   # cv2.INTER_CUBIC (A = -0.75, replicated borders)
+        ops.launches += 1
+        return out
+
+    def _network_eager(self, B, net_h, net_w, cols):
+        import torch
+        ops, w, L = self.ops, self.w, self.ops.L
+        st = _lib.stream_ptr
+        A = _lib
+        h1, w1 = (net_h + 6 - 7) // 2 + 1, (net_w + 6 - 7) // 2 + 1
         x = self._buf('stem', (B, h1, w1, 64))
         ops.gemm(cols, 192, w['stem'][0], 192, B * h1 * w1, 64, 192, act=A.ACT_RELU, bias=w['stem'][1], C=x, ldc=64)
         h, wd = (h1 + 2 - 3) // 2 + 1, (w1 + 2 - 3) // 2 + 1
@@ -887,14 +936,9 @@ class LeresEngine:
         ops.conv3x3(x, B, hh, ww, 128, w['ao3'][0], 32, epi=A.EPI_STORE_F32, bias=w['ao3'][1], X=d32, ldx=32)
         dn = self._buf('dnet', (B, 2 * hh, 2 * ww), torch.float32)
         _lib.check(L.dm_resize_f32_ld(d32.data_ptr(), 32, B, hh, ww, dn.data_ptr(), 2 * hh, 2 * ww, 0, st()), "dm_resize_f32_ld")
-        oh, ow = out_hw if out_hw is not None else (H, W)
-        out = torch.empty(B, oh, ow, dtype=torch.float32, device=self.device)
-        if (oh, ow) == (2 * hh, 2 * ww):
-            out.copy_(dn)                                      # cv2.resize to the same size is a copy
-        else:
-            ops.resize_f32(dn, B, 2 * hh, 2 * ww, out, oh, ow, 1)   # cv2.INTER_CUBIC (A = -0.75, replicated borders)
-        ops.launches += 2
-        return out
+        ops.launches += 1
+        assert (2 * hh, 2 * ww) == (net_h, net_w)
+        return dn
 
     def to(self, device):
         return self

@@ -42,10 +42,25 @@ def main():
     gathered = [all_gather_batch(t, n) for t in mine]
     whole = pipeline(rgb)
     ok = all(torch.equal(g.view(torch.uint8), w.view(torch.uint8)) for g, w in zip(gathered, whole))
+    # BOOST (BASELINE configs[4]): ONE image, its patches dealt to the ranks, the fitted patches exchanged with one
+    # all-gather, every rank replays the blend: must equal the single-rank result bit for bit
+    boost_note = ""
+    if os.environ.get("DIST_CHECK_BOOST", "1") != "0":
+        from depthmap_b200.boost import BoostPipeline, UnetMergeEngine
+        from depthmap_b200.depthmap_generation import LeresEngine
+        pipe = BoostPipeline(LeresEngine(synth_weights.make_leres_state_dict(seed=2), dev),
+                             UnetMergeEngine(synth_weights.make_pix2pix_state_dict(seed=1), dev), dev, 0)
+        img = synth_rgb(300, 420, 12)
+        info = {}
+        sharded = pipe.run(img, 1600, group=dist.group.WORLD, info=info)
+        single = pipe.run(img, 1600)
+        same = np.array_equal(sharded, single)
+        ok = ok and same
+        boost_note = f" boost_patches={len(info['rects'])} boost_equal={same}"
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"dist_check {'ok' if flag.item() == 1 else 'MISMATCH'} world={world} images={n} nccl={'.'.join(map(str, torch.cuda.nccl.version()))}", flush=True)
+        print(f"dist_check {'ok' if flag.item() == 1 else 'MISMATCH'} world={world} images={n}{boost_note} nccl={'.'.join(map(str, torch.cuda.nccl.version()))}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
