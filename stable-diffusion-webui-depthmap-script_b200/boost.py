@@ -405,11 +405,34 @@ class BoostPipeline:
         high = self._estimate_1024(planar, rect, size2)
         return self._post(self._merge(low, high), True)
 
-    def fitted_patch(self, work_img, base, rect, rf):
+    PATCH_BATCH = 8      # crops per LeReS forward in the patch loop (activation memory of the 896 net: ~1.5 GB per crop)
+
+    def fitted_patches(self, work_img, base, rects, rf):
+        """fitted_patch for a list of patches with the base network BATCHED over the crops (all patches use the same two net sizes);
+        yields (mapped, sums) in the order of `rects`.  Engines without `forward_crops` (test doubles) go one by one."""
+        if not hasattr(self.depth, "forward_crops") or self.PATCH_BATCH <= 1:
+            for rect in rects:
+                yield self.fitted_patch(work_img, base, rect, rf)
+            return
+        for c0 in range(0, len(rects), self.PATCH_BATCH):
+            chunk = rects[c0:c0 + self.PATCH_BATCH]
+            low = self.depth.forward_crops(work_img, chunk, rf)
+            high = self.depth.forward_crops(work_img, chunk, 2 * rf)
+            for k, rect in enumerate(chunk):
+                x, y, w, h = rect
+                ests = []
+                for net, src in ((rf, low[k]), (2 * rf, high[k])):      # cubic back to the crop's size (estimateleres), then to 1024^2 (doubleestimate)
+                    at_crop = self._cubic(src.data_ptr(), net, net, net, h, w)
+                    ests.append(self._cubic(at_crop.data_ptr(), w, h, w, PIX2PIX_SIZE, PIX2PIX_SIZE))
+                est = self._post(self._merge(ests[0], ests[1]), True)
+                yield self.fitted_patch(work_img, base, rect, rf, est=est)
+
+    def fitted_patch(self, work_img, base, rect, rf, est=None):
         """the network part of one patch: -> (mapped [1024, 1024], fit partial sums); independent of every other patch"""
         import torch
         x, y, w, h = rect
-        est = self.double_estimate(work_img, rect, rf, 2 * rf)
+        if est is None:
+            est = self.double_estimate(work_img, rect, rf, 2 * rf)
         pitch = int(base.shape[1])
         base1024 = self._cubic(base.data_ptr() + 4 * (y * pitch + x), pitch, h, w, PIX2PIX_SIZE, PIX2PIX_SIZE)
         mapped = self._post(self._merge(base1024, est), False)
@@ -455,8 +478,7 @@ class BoostPipeline:
         rects = p["scaled_rects"]
         world, rank = (group.size(), group.rank()) if group is not None else (1, 0)
         if world == 1:
-            for rect in rects:
-                mapped, sums = self.fitted_patch(work, base, rect, rf)
+            for rect, (mapped, sums) in zip(rects, self.fitted_patches(work, base, rects, rf)):
                 self.blend(updated, mapped, sums, rect)
         else:
             import torch.distributed as dist
@@ -464,8 +486,7 @@ class BoostPipeline:
             per = -(-len(rects) // world)
             send_m = torch.zeros(per, PIX2PIX_SIZE * PIX2PIX_SIZE, dtype=torch.float32, device=self.device)
             send_s = torch.zeros(per, self.P * 4, dtype=torch.float64, device=self.device)
-            for slot, i in enumerate(mine):
-                mapped, sums = self.fitted_patch(work, base, rects[i], rf)
+            for slot, (mapped, sums) in enumerate(self.fitted_patches(work, base, [rects[i] for i in mine], rf)):
                 send_m[slot].copy_(mapped.view(-1))
                 send_s[slot].copy_(sums)
             all_m = torch.empty(world * per, PIX2PIX_SIZE * PIX2PIX_SIZE, dtype=torch.float32, device=self.device)

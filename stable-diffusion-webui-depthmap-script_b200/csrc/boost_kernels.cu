@@ -338,8 +338,9 @@ __global__ void __launch_bounds__(256) boost_u8_to_planar_kernel(const uint8_t *
 // ---- LeReS stem for a crop of a planar fp32 image ---------------------------------------------------------------------------
 struct StemF32Params {
     const float *img;       // [3, Hi, Wi] (network channel order), values as handed to estimateleres (no / 255)
+    const int *rects;       // optional [B][4] = x0, y0, w, h per batch item (device memory): B crops of the same image in one launch
     long long plane;
-    int pitch, x0, y0, w, h, nh, nw, Ho, Wo;
+    int B, pitch, x0, y0, w, h, nh, nw, Ho, Wo;
     float mean[3], inv_std[3];
     __half *out;            // [Ho*Wo, 192]
 };
@@ -355,10 +356,14 @@ __device__ __forceinline__ void cv_linear_coord_f(int d, float scale, int n_src,
 
 __global__ void __launch_bounds__(256) leres_stem_im2col_f32_kernel(StemF32Params p) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)p.Ho * p.Wo * 8) return;
+    if (idx >= (long long)p.B * p.Ho * p.Wo * 8) return;
     const int ky = (int)(idx & 7);
     const long long pix = idx >> 3;
-    const int ox = (int)(pix % p.Wo), oy = (int)(pix / p.Wo);
+    const int ox = (int)(pix % p.Wo), oy = (int)((pix / p.Wo) % p.Ho);
+    if (p.rects) {
+        const int4 r = __ldg(reinterpret_cast<const int4 *>(p.rects) + (int)(pix / ((long long)p.Wo * p.Ho)));
+        p.x0 = r.x; p.y0 = r.y; p.w = r.z; p.h = r.w;
+    }
     __half *row = p.out + pix * 192;
     if (ky == 7) {
         for (int k = 147; k < 192; ++k) row[k] = __float2half_rn(0.f);
@@ -506,11 +511,28 @@ DM_EXPORT int dm_leres_stem_im2col_f32(const float *img, int Hi, int Wi, int x0,
     using namespace dm;
     if (!img || !out || x0 < 0 || y0 < 0 || w <= 0 || h <= 0 || x0 + w > Wi || y0 + h > Hi) { set_error("dm_leres_stem_im2col_f32: crop outside the image"); return DM_E_INVALID; }
     StemF32Params p;
+    p.rects = nullptr; p.B = 1;
     p.img = img; p.plane = (long long)Hi * Wi; p.pitch = Wi; p.x0 = x0; p.y0 = y0; p.w = w; p.h = h; p.nh = net_h; p.nw = net_w;
     p.Ho = (net_h + 6 - 7) / 2 + 1; p.Wo = (net_w + 6 - 7) / 2 + 1;
     for (int c = 0; c < 3; ++c) { p.mean[c] = mean_host[c]; p.inv_std[c] = 1.0f / std_host[c]; }
     p.out = (__half *)out;
     leres_stem_im2col_f32_kernel<<<GRID((long long)p.Ho * p.Wo * 8), 256, 0, (cudaStream_t)stream_>>>(p);
+    DM_LAUNCH_CHECK("leres_stem_im2col_f32_kernel");
+    return DM_OK;
+}
+
+/* B crops of the same planar image in one launch; rects: device int32 [B][4] = x0, y0, w, h (validated by the caller) */
+DM_EXPORT int dm_leres_stem_im2col_f32_batch(const float *img, int Hi, int Wi, const int *rects_dev, int B, int net_h, int net_w, const float *mean_host,
+                                             const float *std_host, void *out, void *stream_) {
+    using namespace dm;
+    if (!img || !out || !rects_dev || B <= 0) { set_error("dm_leres_stem_im2col_f32_batch: bad arguments"); return DM_E_INVALID; }
+    StemF32Params p;
+    p.rects = rects_dev; p.B = B;
+    p.img = img; p.plane = (long long)Hi * Wi; p.pitch = Wi; p.x0 = 0; p.y0 = 0; p.w = Wi; p.h = Hi; p.nh = net_h; p.nw = net_w;
+    p.Ho = (net_h + 6 - 7) / 2 + 1; p.Wo = (net_w + 6 - 7) / 2 + 1;
+    for (int c = 0; c < 3; ++c) { p.mean[c] = mean_host[c]; p.inv_std[c] = 1.0f / std_host[c]; }
+    p.out = (__half *)out;
+    leres_stem_im2col_f32_kernel<<<GRID((long long)B * p.Ho * p.Wo * 8), 256, 0, (cudaStream_t)stream_>>>(p);
     DM_LAUNCH_CHECK("leres_stem_im2col_f32_kernel");
     return DM_OK;
 }

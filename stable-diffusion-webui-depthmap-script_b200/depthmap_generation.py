@@ -848,6 +848,28 @@ class LeresEngine:
         ops.launches += 1
         return out
 
+    def forward_crops(self, planar, rects, net):
+        """BOOST's patch batch: estimateleres' network on B crops of one planar fp32 image ([3, Hi, Wi], rects = [(x0, y0, w, h)]), all at the
+        same square net size -> fp32 [B, net, net] (a pooled buffer, valid until the next call at this (B, net)); the caller does the
+        per-crop resize back (each crop has its own size)."""
+        import torch
+        if net % 32:
+            raise ValueError("LeReS needs a net size that is a multiple of 32")
+        B = len(rects)
+        hi, wi = int(planar.shape[1]), int(planar.shape[2])
+        for x0, y0, w, h in rects:
+            if x0 < 0 or y0 < 0 or w <= 0 or h <= 0 or x0 + w > wi or y0 + h > hi:
+                raise ValueError(f"crop {(x0, y0, w, h)} outside the {wi}x{hi} image")
+        r = torch.tensor([list(map(int, q)) for q in rects], dtype=torch.int32).to(self.device)
+        h1 = (net + 6 - 7) // 2 + 1
+        cols = self._buf('stem_cols', (B * h1 * h1, 192))
+        m = (ctypes.c_float * 3)(*self.MEAN)
+        sdev = (ctypes.c_float * 3)(*self.STD)
+        _lib.check(self.ops.L.dm_leres_stem_im2col_f32_batch(planar.data_ptr(), hi, wi, r.data_ptr(), B, net, net, m, sdev, cols.data_ptr(), _lib.stream_ptr()),
+                   "dm_leres_stem_im2col_f32_batch")
+        self.ops.launches += 1
+        return self._network(B, net, net, cols)
+
     def _network_eager(self, B, net_h, net_w, cols):
         import torch
         ops, w, L = self.ops, self.w, self.ops.L
