@@ -298,6 +298,10 @@ int dm_unet_up_cols(const float *skip, int C1, const float *up, int C2, int H, i
                     void *stream);
 int dm_unet_interleave(const float *tmp /*[4][H*W,N]*/, int H, int W, int N, int C, float *out /*[2H,2W,C]*/, void *stream);
 int dm_unet_final(const float *tmp /*[4][H*W,N]*/, int H, int W, int N, float bias, float *out /*[2H,2W]*/, void *stream);
+/* the two single-/two-channel ends of the U-Net as direct fp32 kernels (no columns, no GEMM): outermost conv 2 -> 64 (w: [64][32], columns
+ * (ky, kx, cin)) and outermost transposed conv (C1 + C2) -> 1 + bias + tanh (w: [4 parities][4 taps][C1 + C2]) */
+int dm_unet_first(const float *x /*[H,W,2]*/, int H, int W, const float *w, float *out /*[H/2,W/2,64]*/, void *stream);
+int dm_unet_last(const float *skip, int C1, const float *up, int C2, int H, int W, const float *w, float bias, float *out /*[2H,2W]*/, void *stream);
 /* out[m, n] = gamma[n] * sum over chunks c (in order) of ws[c][m, n]: the depth chunks of a split-operand GEMM */
 int dm_sum_chunks_f32(const float *ws, int nchunks, long long mn, int N, const float *gamma, float *out, void *stream);
 int dm_boost_minmax(const float *x, long long n, float *partial /*[partials][2]*/, void *stream);

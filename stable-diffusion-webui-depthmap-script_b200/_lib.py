@@ -78,7 +78,7 @@ EXPORTS = [
     "dm_video_select_pick", "dm_video_select_bounds", "dm_video_scale_f64",
     "dm_model_create", "dm_model_destroy", "dm_model_net_size", "dm_model_launches", "dm_depth_forward", "dm_dinov2_pos_embed", "dm_beit_rel_table", "dm_vit_pos_embed",
     "dm_leres_stem_im2col", "dm_maxpool3x3s2_nhwc_f16", "dm_subsample2_nhwc_f16", "dm_add_f16", "dm_resize_f32_ld",
-    "dm_boost_partials", "dm_unet_first_cols", "dm_unet_down_cols", "dm_unet_up_cols", "dm_unet_interleave", "dm_unet_final", "dm_sum_chunks_f32", "dm_boost_minmax",
+    "dm_boost_partials", "dm_unet_first_cols", "dm_unet_down_cols", "dm_unet_up_cols", "dm_unet_interleave", "dm_unet_final", "dm_unet_first", "dm_unet_last", "dm_sum_chunks_f32", "dm_boost_minmax",
     "dm_boost_merge_input", "dm_boost_post", "dm_boost_fit_sums", "dm_boost_blend", "dm_boost_resize_cubic", "dm_boost_u8_to_planar",
     "dm_leres_stem_im2col_f32", "dm_leres_stem_im2col_f32_batch",
 ]
@@ -176,6 +176,8 @@ def _bind_optional(L):
         L.dm_unet_final.argtypes = [vp, i32, i32, i32, f32, vp, vp]
         L.dm_boost_minmax.argtypes = [vp, ll, vp, vp]
         L.dm_sum_chunks_f32.argtypes = [vp, i32, ll, i32, vp, vp, vp]
+        L.dm_unet_first.argtypes = [vp, i32, i32, vp, vp, vp]
+        L.dm_unet_last.argtypes = [vp, i32, vp, i32, i32, i32, vp, f32, vp, vp]
         L.dm_boost_merge_input.argtypes = [vp, vp, ll, vp, vp, vp, vp]
         L.dm_boost_post.argtypes = [vp, ll, vp, i32, vp, vp]
         L.dm_boost_fit_sums.argtypes = [vp, vp, ll, vp, vp]

@@ -202,6 +202,14 @@ class UnetMergeEngine:
             self.up.append((per_parity, cout))
             if d == 0:
                 self.bias = float(sd[prefix + "model.3.bias"].detach().float().item())
+                # the two ends of the network as direct fp32 kernels (split mode): 2 -> 64 conv and (64 + 64) -> 1 transposed conv
+                self.first_w = wd.permute(0, 2, 3, 1).reshape(64, 32).contiguous()
+                par = []
+                for a in (0, 1):
+                    for b in (0, 1):
+                        ky, kx = ((1, 3), (0, 2))[a], ((1, 3), (0, 2))[b]
+                        par.append(torch.stack([wu[:, 0, ky[ty], kx[tx]] for ty in (0, 1) for tx in (0, 1)], dim=0))     # [4 taps, Cin_total]
+                self.last_w = torch.stack(par, dim=0).contiguous()                                                    # [4, 4, 128]
             prefix = child
         self._bufs = {}
         # every call has the same shapes: after one eager call (allocations) the ~600 launches of a forward are captured into a CUDA
@@ -308,6 +316,12 @@ class UnetMergeEngine:
             cin, cout = self.CH[d]
             M = (Hin // 2) ** 2
             K = (64 if d == 0 else 16 * cin) * cp
+            if d == 0 and self.split:
+                out = self._buf("h0", (M, cout), torch.float32)
+                _lib.check(L.dm_unet_first(x2.data_ptr(), Hin, Hin, self.first_w.data_ptr(), out.data_ptr(), st()), "dm_unet_first")
+                ops.launches += 1
+                h.append(out)
+                continue
             cols = self._buf("cols", (M, K), torch.float16)
             if d == 0:
                 _lib.check(L.dm_unet_first_cols(x2.data_ptr(), Hin, Hin, cols.data_ptr(), int(self.split), st()), "dm_unet_first_cols")
@@ -322,6 +336,11 @@ class UnetMergeEngine:
             Hs = S >> (d + 1)
             M = Hs * Hs
             c1 = self.CH[d][1]
+            if d == 0 and self.split:
+                out = torch.empty(2 * Hs, 2 * Hs, dtype=torch.float32, device=self.device)
+                _lib.check(L.dm_unet_last(h[0].data_ptr(), c1, u.data_ptr(), cu, Hs, Hs, self.last_w.data_ptr(), self.bias, out.data_ptr(), st()), "dm_unet_last")
+                ops.launches += 1
+                break
             K = 4 * (c1 + cu) * cp
             cols = self._buf("cols", (4, M, K), torch.float16)
             _lib.check(L.dm_unet_up_cols(h[d].data_ptr(), c1, u.data_ptr() if u is not None else None, cu, Hs, Hs, cols.data_ptr(), int(self.split), st()),

@@ -161,6 +161,81 @@ __global__ void __launch_bounds__(256) sum_chunks_kernel(const float *__restrict
     *reinterpret_cast<float4 *>(out + i4) = make_float4(acc.x * g.x, acc.y * g.y, acc.z * g.z, acc.w * g.w);
 }
 
+// The outermost transposed convolution has ONE output channel: as a GEMM it is 3.2 GB of split columns for a [.., 32]-padded result.
+// Direct form in exact fp32: one thread per output pixel (2y + a, 2x + b), its four taps x (C1 + C2) input channels against the parity's
+// filter slice in shared memory (broadcast reads), ReLU on load, bias + tanh.  w: [4 parities][4 taps][C1 + C2].
+__global__ void __launch_bounds__(256) unet_last_kernel(const float *__restrict__ skip, int C1, const float *__restrict__ up, int C2, int H, int W,
+                                                        const float *__restrict__ w, float bias, float *__restrict__ out) {
+    extern __shared__ float s_w[];                      // [4][4][C]
+    const int C = C1 + C2;
+    for (int i = threadIdx.x; i < 16 * C; i += 256) s_w[i] = w[i];
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= 4ll * H * W) return;
+    const int ox = (int)(idx % (2 * W)), oy = (int)(idx / (2 * W));
+    const int a = oy & 1, b = ox & 1, y = oy >> 1, x = ox >> 1;
+    const float *wp = s_w + ((a << 1) | b) * 4 * C;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+        const int ty = tap >> 1, tx = tap & 1;
+        const int iy = y + (a == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0));
+        const int ix = x + (b == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0));
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        const float4 *p1 = reinterpret_cast<const float4 *>(skip + ((long long)iy * W + ix) * C1);
+        const float4 *wt = reinterpret_cast<const float4 *>(wp + tap * C);
+        for (int c = 0; c < C1 / 4; ++c) {
+            const float4 v = __ldg(p1 + c), f = wt[c];
+            acc0 = fmaf(fmaxf(v.x, 0.f), f.x, acc0); acc1 = fmaf(fmaxf(v.y, 0.f), f.y, acc1);
+            acc2 = fmaf(fmaxf(v.z, 0.f), f.z, acc2); acc3 = fmaf(fmaxf(v.w, 0.f), f.w, acc3);
+        }
+        const float4 *p2 = reinterpret_cast<const float4 *>(up + ((long long)iy * W + ix) * C2);
+        wt += C1 / 4;
+        for (int c = 0; c < C2 / 4; ++c) {
+            const float4 v = __ldg(p2 + c), f = wt[c];
+            acc0 = fmaf(fmaxf(v.x, 0.f), f.x, acc0); acc1 = fmaf(fmaxf(v.y, 0.f), f.y, acc1);
+            acc2 = fmaf(fmaxf(v.z, 0.f), f.z, acc2); acc3 = fmaf(fmaxf(v.w, 0.f), f.w, acc3);
+        }
+    }
+    out[idx] = tanhf((acc0 + acc1) + (acc2 + acc3) + bias);
+}
+
+// The outermost convolution (2 -> 64 channels, 4x4 stride 2, no activation in front): direct fp32, one thread per (output pixel, 8 channels).
+// w: [64][32] with columns (ky, kx, cin)
+__global__ void __launch_bounds__(256) unet_first_kernel(const float *__restrict__ x, int H, int W, const float *__restrict__ w, float *__restrict__ out) {
+    __shared__ float s_w[64 * 32];
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) s_w[i] = w[i];
+    __syncthreads();
+    const int Ho = H / 2, Wo = W / 2;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)Ho * Wo * 8) return;
+    const int cg = (int)(idx & 7);
+    const long long pix = idx >> 3;
+    const int ox = (int)(pix % Wo), oy = (int)(pix / Wo);
+    float v[32];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+            const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+            float2 p = make_float2(0.f, 0.f);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) p = __ldg(reinterpret_cast<const float2 *>(x + ((long long)iy * W + ix) * 2));
+            v[(ky * 4 + kx) * 2] = p.x; v[(ky * 4 + kx) * 2 + 1] = p.y;
+        }
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float *wr = s_w + (cg * 8 + c) * 32;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc = fmaf(v[k], wr[k], acc);
+        o[c] = acc;
+    }
+    float4 *dst = reinterpret_cast<float4 *>(out + pix * 64 + cg * 8);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
 // ---- reductions ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) boost_minmax_kernel(const float *__restrict__ x, long long n, float *__restrict__ partial) {
     float lo = INFINITY, hi = -INFINITY;
@@ -435,6 +510,22 @@ DM_EXPORT int dm_unet_final(const float *tmp, int H, int W, int N, float bias, f
     if (!tmp || !out) { set_error("dm_unet_final: null argument"); return DM_E_INVALID; }
     unet_final_kernel<<<GRID(4ll * H * W), 256, 0, (cudaStream_t)stream_>>>(tmp, H, W, N, bias, out);
     DM_LAUNCH_CHECK("unet_final_kernel");
+    return DM_OK;
+}
+
+DM_EXPORT int dm_unet_last(const float *skip, int C1, const float *up, int C2, int H, int W, const float *w, float bias, float *out, void *stream_) {
+    using namespace dm;
+    if (!skip || !up || !w || !out || (C1 % 4) || (C2 % 4) || 16 * (C1 + C2) * 4 > 48 * 1024) { set_error("dm_unet_last: bad arguments"); return DM_E_INVALID; }
+    unet_last_kernel<<<GRID(4ll * H * W), 256, 16 * (C1 + C2) * sizeof(float), (cudaStream_t)stream_>>>(skip, C1, up, C2, H, W, w, bias, out);
+    DM_LAUNCH_CHECK("unet_last_kernel");
+    return DM_OK;
+}
+
+DM_EXPORT int dm_unet_first(const float *x, int H, int W, const float *w, float *out, void *stream_) {
+    using namespace dm;
+    if (!x || !w || !out || (H & 1) || (W & 1)) { set_error("dm_unet_first: bad arguments"); return DM_E_INVALID; }
+    unet_first_kernel<<<GRID((long long)(H / 2) * (W / 2) * 8), 256, 0, (cudaStream_t)stream_>>>(x, H, W, w, out);
+    DM_LAUNCH_CHECK("unet_first_kernel");
     return DM_OK;
 }
 
