@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(256) unet_last_kernel(const float *__restrict_
 // The outermost convolution (2 -> 64 channels, 4x4 stride 2, no activation in front): direct fp32, one thread per (output pixel, 8 channels).
 // w: [64][32] with columns (ky, kx, cin)
 __global__ void __launch_bounds__(256) unet_first_kernel(const float *__restrict__ x, int H, int W, const float *__restrict__ w, float *__restrict__ out) {
-    __shared__ float s_w[64 * 32];
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) s_w[i] = w[i];
+    __shared__ __align__(16) float s_w[32 * 64];       // transposed to [k][channel]: the 8 channel groups of a warp read 8 distinct 32-byte segments
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) s_w[(i & 31) * 64 + (i >> 5)] = w[i];
     __syncthreads();
     const int Ho = H / 2, Wo = W / 2;
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -222,14 +222,12 @@ __global__ void __launch_bounds__(256) unet_first_kernel(const float *__restrict
             if (iy >= 0 && iy < H && ix >= 0 && ix < W) p = __ldg(reinterpret_cast<const float2 *>(x + ((long long)iy * W + ix) * 2));
             v[(ky * 4 + kx) * 2] = p.x; v[(ky * 4 + kx) * 2 + 1] = p.y;
         }
-    float o[8];
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float *wr = s_w + (cg * 8 + c) * 32;
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) acc = fmaf(v[k], wr[k], acc);
-        o[c] = acc;
+    for (int k = 0; k < 32; ++k) {                     // ascending k per channel: the same summation order as before
+        const float4 w0 = *reinterpret_cast<const float4 *>(s_w + k * 64 + cg * 8), w1 = *reinterpret_cast<const float4 *>(s_w + k * 64 + cg * 8 + 4);
+        o[0] = fmaf(v[k], w0.x, o[0]); o[1] = fmaf(v[k], w0.y, o[1]); o[2] = fmaf(v[k], w0.z, o[2]); o[3] = fmaf(v[k], w0.w, o[3]);
+        o[4] = fmaf(v[k], w1.x, o[4]); o[5] = fmaf(v[k], w1.y, o[5]); o[6] = fmaf(v[k], w1.z, o[6]); o[7] = fmaf(v[k], w1.w, o[7]);
     }
     float4 *dst = reinterpret_cast<float4 *>(out + pix * 64 + cg * 8);
     dst[0] = make_float4(o[0], o[1], o[2], o[3]);

@@ -21,6 +21,16 @@ def main():
         eng = UnetMergeEngine(synth_weights.make_pix2pix_state_dict(seed=1), dev)
         x2 = torch.rand(1024, 1024, 2, device=dev) * 2 - 1
         fn = lambda: eng.forward(x2)
+    elif which == "patch":          # one BOOST patch: LeReS at 448 / 896, two merge-net forwards and every glue kernel, all eager
+        from depthmap_b200.boost import BoostPipeline
+        pipe = BoostPipeline(LeresEngine(synth_weights.make_leres_state_dict(seed=2), dev), UnetMergeEngine(synth_weights.make_pix2pix_state_dict(seed=1), dev), dev, 0)
+        img = torch.rand(3, 1024, 1024, device=dev)
+        base = torch.rand(1024, 1024, device=dev)
+        upd = base.clone()
+
+        def fn():
+            mapped, sums = pipe.fitted_patch(img, base, (100, 100, 600, 600), 448)
+            pipe.blend(upd, mapped, sums, (100, 100, 600, 600))
     else:
         eng = LeresEngine(synth_weights.make_leres_state_dict(seed=2), dev)
         img = torch.rand(3, 1024, 1024, device=dev)
