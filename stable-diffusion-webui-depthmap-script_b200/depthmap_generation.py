@@ -1446,6 +1446,11 @@ class ModelHolder:
         """uint8 CUDA [B,H,W,3] -> (float32 CUDA [B,H,W], invert flag).  Batched form of get_raw_prediction."""
         if self.depth_model is None:
             raise RuntimeError("no depth model loaded; call ensure_models first")
+        if self.pix2pix_model is not None:
+            # boost: estimateboost works on one image at a time (its resolutions and patches depend on the image); the net size is ignored
+            import torch
+            preds = [self.pix2pix_model.run(rgb[i].cpu().numpy(), self.boost_rmax, to_host=False) for i in range(rgb.shape[0])]
+            return torch.stack(preds), self.depth_model_type in [0, 7, 8, 9, 10]
         if self.depth_model_type in (0, 1, 2, 3, 9, 12, 13, 14):
             pred = self.depth_model.forward_batch(rgb, net_width, net_height)
         else:

@@ -161,3 +161,31 @@ def test_modelholder_boost_api(cuda_device):
         mh.ensure_models(12, cuda_device, True)
     mh.unload_models()
     assert mh.pix2pix_model is None
+
+
+def test_funnel_with_boost(cuda_device):
+    """core_generation_funnel(..., BOOST=True, model type 0): the depth prediction the funnel yields is estimateboost's (not the plain
+    LeReS forward), and the u16 depth / stereo that follow are computed from it (reference src/core.py:130,185-211)."""
+    from PIL import Image
+    from depthmap_b200 import core
+    from oracle import synth_weights
+    lsd = synth_weights.make_leres_state_dict(seed=2)
+    psd = synth_weights.make_pix2pix_state_dict(seed=1)
+    holder = core.get_model_holder()
+    holder.unload_models()
+    holder.weights_provider = lambda t: psd if t == "pix2pix" else lsd
+    try:
+        img = synth_rgb(256, 320, 4)
+        inp = dict(compute_device='GPU', model_type=0, net_width=448, net_height=448, boost=True, do_output_depth=True,
+                   do_output_depth_prediction=True, gen_stereo=True, stereo_modes=['left-right'], gen_normalmap=False)
+        out = list(core.core_generation_funnel(None, [Image.fromarray(img)], None, None, inp, ops={'boost_rmax': 1000}))
+        assert [k for _, k, _ in out] == ['depth_prediction', 'depth', 'left-right']
+        pred = out[0][2]
+        direct = holder.pix2pix_model.run(img, 1000)
+        assert pred.shape == (256, 320) and np.array_equal(pred, -direct)          # src/core.py:186-195: `out = -raw_prediction` for the "invert" models, and that is what is yielded
+        plain = holder.depth_model.forward_batch(__import__("torch").from_numpy(img).to(cuda_device).unsqueeze(0), 448, 448)[0].cpu().numpy()
+        assert np.abs(plain - direct).max() > 1e-3 * (plain.max() - plain.min())        # boost really ran
+        assert out[1][2].size == (320, 256) and out[2][2].size == (640, 256)
+    finally:
+        holder.unload_models()
+        holder.weights_provider = None
