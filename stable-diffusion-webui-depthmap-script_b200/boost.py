@@ -164,7 +164,7 @@ class UnetMergeEngine:
 
     CH = [(2, 64), (64, 128), (128, 256), (256, 512)] + [(512, 512)] * 6      # (in, out) of the down conv at depth d
 
-    KC = 1024      # GEMM depth per launch in split mode; partial products are summed in fp32 by the epilogue (X += acc), see _gemm
+    KC = 1024      # GEMM depth per launch in split mode; the chunks' partial products are added in fp32 by dm_sum_chunks_f32, see _gemms
 
     def __init__(self, state_dict, device, split=True, kc=KC):
         import torch
@@ -496,7 +496,7 @@ class BoostPipeline:
         updated = base.clone()
         rects = p["scaled_rects"]
         world, rank = (group.size(), group.rank()) if group is not None else (1, 0)
-        if world == 1:
+        if world == 1 or not rects:         # no patch selected (flat or small image): the result is the resized whole-image estimate
             for rect, (mapped, sums) in zip(rects, self.fitted_patches(work, base, rects, rf)):
                 self.blend(updated, mapped, sums, rect)
         else:

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) unet_first_cols_kernel(const float *__res
     const int Ho = H / 2, Wo = W / 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)Ho * Wo * 8) return;
-    const int part = (int)(idx & 7);            // 8 columns each: parts 0-3 = two taps rows... (4 taps x 2 channels), parts 4-7 = zero padding
+    const int part = (int)(idx & 7);            // 8 columns each: parts 0-3 = kernel row ky (4 taps x 2 channels), parts 4-7 = zero padding
     const long long pix = idx >> 3;
     const int ox = (int)(pix % Wo), oy = (int)(pix / Wo);
     float v[8];
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) unet_first_cols_kernel(const float *__res
     split_store8(v, row, row + 64, row + 128, split != 0);
 }
 
-// act: 1 = LeakyReLU(0.2)
+// LeakyReLU(0.2) is applied while gathering (every down convolution but the outermost has one in front)
 __global__ void __launch_bounds__(256) unet_down_cols_kernel(const float *__restrict__ x, int H, int W, int C, __half *__restrict__ out, int split) {
     const int Ho = H / 2, Wo = W / 2, c8 = C >> 3;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

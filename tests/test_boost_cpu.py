@@ -51,3 +51,14 @@ def test_receptive_fields():
     from oracle import boost as ob
     for t in range(15):
         assert boost.receptive_field(t) == ob.receptive_field(t)
+
+
+def test_plan_without_patches():
+    """an image smaller than the patch grid selects nothing: estimateboost then returns the resized whole-image double estimate"""
+    from depthmap_b200 import boost
+    from oracle import boost as ob
+    img = _img(200, 200, 3)
+    p = boost.plan(img, 0, 1600)
+    assert p["rects"] == [] and p["scaled_rects"] == []
+    whole, patch_scale = ob.calculateprocessingres(img, 448, 0.2, 3, 1600)
+    assert p["whole"] == whole
