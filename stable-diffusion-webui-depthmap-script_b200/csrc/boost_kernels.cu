@@ -427,41 +427,53 @@ __device__ __forceinline__ void cv_linear_coord_f(int d, float scale, int n_src,
     i0 = sx; i1 = min(sx + 1, n_src - 1); f = fx;
 }
 
+__device__ __forceinline__ void stem_flush_rows_f32(const __half *s_rows, __half *out, long long first_pix, long long total_pix) {
+    const long long rows = min((long long)32, total_pix - first_pix);
+    const uint4 *src = reinterpret_cast<const uint4 *>(s_rows);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + first_pix * 192);
+    for (int i = threadIdx.x; i < (int)rows * 24; i += 256) dst[i] = src[i];
+}
+
+// rows assembled in shared memory and written with 16-byte stores (see leres_kernels.cu)
 __global__ void __launch_bounds__(256) leres_stem_im2col_f32_kernel(StemF32Params p) {
+    __shared__ __align__(16) __half s_rows[32 * 192];
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)p.B * p.Ho * p.Wo * 8) return;
+    const long long total_pix = (long long)p.B * p.Ho * p.Wo;
     const int ky = (int)(idx & 7);
     const long long pix = idx >> 3;
-    const int ox = (int)(pix % p.Wo), oy = (int)((pix / p.Wo) % p.Ho);
-    if (p.rects) {
-        const int4 r = __ldg(reinterpret_cast<const int4 *>(p.rects) + (int)(pix / ((long long)p.Wo * p.Ho)));
-        p.x0 = r.x; p.y0 = r.y; p.w = r.z; p.h = r.w;
-    }
-    __half *row = p.out + pix * 192;
-    if (ky == 7) {
+    const bool live = pix < total_pix;
+    __half *row = s_rows + (threadIdx.x >> 3) * 192;
+    if (live && ky == 7) {
         for (int k = 147; k < 192; ++k) row[k] = __float2half_rn(0.f);
-        return;
-    }
-    const bool identity = p.nh == p.h && p.nw == p.w;
-    const float sy = (float)p.h / (float)p.nh, sx = (float)p.w / (float)p.nw;
-    const int iy = oy * 2 - 3 + ky;
-    for (int kx = 0; kx < 7; ++kx) {
-        const int ix = ox * 2 - 3 + kx;
-        float v[3] = {0.f, 0.f, 0.f};
-        if (iy >= 0 && iy < p.nh && ix >= 0 && ix < p.nw) {
-            int y0 = iy, y1 = iy, x0 = ix, x1 = ix; float fy = 0.f, fx = 0.f;
-            if (!identity) { cv_linear_coord_f(iy, sy, p.h, y0, y1, fy); cv_linear_coord_f(ix, sx, p.w, x0, x1, fx); }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float *pl = p.img + c * p.plane + (long long)p.y0 * p.pitch + p.x0;
-                const float a = pl[(long long)y0 * p.pitch + x0] * (1.f - fx) + pl[(long long)y0 * p.pitch + x1] * fx;
-                const float d = pl[(long long)y1 * p.pitch + x0] * (1.f - fx) + pl[(long long)y1 * p.pitch + x1] * fx;
-                v[c] = ((a * (1.f - fy) + d * fy) - p.mean[c]) * p.inv_std[c];
-            }
+    } else if (live) {
+        const int ox = (int)(pix % p.Wo), oy = (int)((pix / p.Wo) % p.Ho);
+        if (p.rects) {
+            const int4 r = __ldg(reinterpret_cast<const int4 *>(p.rects) + (int)(pix / ((long long)p.Wo * p.Ho)));
+            p.x0 = r.x; p.y0 = r.y; p.w = r.z; p.h = r.w;
         }
+        const bool identity = p.nh == p.h && p.nw == p.w;
+        const float sy = (float)p.h / (float)p.nh, sx = (float)p.w / (float)p.nw;
+        const int iy = oy * 2 - 3 + ky;
+        for (int kx = 0; kx < 7; ++kx) {
+            const int ix = ox * 2 - 3 + kx;
+            float v[3] = {0.f, 0.f, 0.f};
+            if (iy >= 0 && iy < p.nh && ix >= 0 && ix < p.nw) {
+                int y0 = iy, y1 = iy, x0 = ix, x1 = ix; float fy = 0.f, fx = 0.f;
+                if (!identity) { cv_linear_coord_f(iy, sy, p.h, y0, y1, fy); cv_linear_coord_f(ix, sx, p.w, x0, x1, fx); }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) row[(ky * 7 + kx) * 3 + c] = __float2half_rn(v[c]);
+                for (int c = 0; c < 3; ++c) {
+                    const float *pl = p.img + c * p.plane + (long long)p.y0 * p.pitch + p.x0;
+                    const float a = pl[(long long)y0 * p.pitch + x0] * (1.f - fx) + pl[(long long)y0 * p.pitch + x1] * fx;
+                    const float d = pl[(long long)y1 * p.pitch + x0] * (1.f - fx) + pl[(long long)y1 * p.pitch + x1] * fx;
+                    v[c] = ((a * (1.f - fy) + d * fy) - p.mean[c]) * p.inv_std[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) row[(ky * 7 + kx) * 3 + c] = __float2half_rn(v[c]);
+        }
     }
+    __syncthreads();
+    stem_flush_rows_f32(s_rows, p.out, (long long)blockIdx.x * 32, total_pix);
 }
 
 }  // namespace dm
