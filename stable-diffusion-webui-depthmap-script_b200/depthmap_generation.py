@@ -697,6 +697,7 @@ class LeresEngine:
         self.ops = _Ops()
         self._bufs, self._buf_key = {}, None
         self._graphs, self._graph_calls = {}, {}
+        self._pooled_bytes, self._pool_limit = 0, None
         self._use_graph = os.environ.get("DEPTHMAP_B200_LERES_GRAPH", "1") != "0"
         self._pack(state_dict)
 
@@ -779,7 +780,23 @@ class LeresEngine:
         if t is None:
             t = torch.empty(*shape, dtype=dtype, device=self.device)
             self._bufs[key] = t
+            self._pooled_bytes += t.numel() * t.element_size()
         return t
+
+    def _trim_pools(self):
+        """Called at the start of a forward, never inside one: BOOST's whole-image net size depends on the image, so a long run would
+        otherwise collect one buffer set (and one graph) per size.  Past half of the device memory everything pooled is dropped and
+        rebuilt lazily."""
+        import torch
+        if self._pool_limit is None:
+            self._pool_limit = torch.cuda.get_device_properties(self.device).total_memory // 2
+        if self._pooled_bytes > self._pool_limit and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.synchronize(self.device)
+            self._graphs.clear()
+            self._graph_calls.clear()
+            self._bufs.clear()
+            self._pooled_bytes = 0
+            torch.cuda.empty_cache()
 
     # ---- forward ---------------------------------------------------------------------------------------------------
     def _network(self, B, net_h, net_w, cols):
@@ -827,6 +844,7 @@ class LeresEngine:
         net_h = net_h if net_h is not None else net_w
         if net_w % 32 or net_h % 32:
             raise ValueError("LeReS needs a net size that is a multiple of 32")
+        self._trim_pools()
         # stem: pre-processing + im2col of the 7x7 / 2 conv, folded BN + ReLU in the GEMM, max-pool
         h1, w1 = (net_h + 6 - 7) // 2 + 1, (net_w + 6 - 7) // 2 + 1
         cols = self._buf('stem_cols', (B * h1 * w1, 192))
@@ -856,6 +874,7 @@ class LeresEngine:
         if net % 32:
             raise ValueError("LeReS needs a net size that is a multiple of 32")
         B = len(rects)
+        self._trim_pools()
         hi, wi = int(planar.shape[1]), int(planar.shape[2])
         for x0, y0, w, h in rects:
             if x0 < 0 or y0 < 0 or w <= 0 or h <= 0 or x0 + w > wi or y0 + h > hi:
