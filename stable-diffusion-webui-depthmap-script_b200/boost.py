@@ -500,20 +500,14 @@ class BoostPipeline:
             for rect, (mapped, sums) in zip(rects, self.fitted_patches(work, base, rects, rf)):
                 self.blend(updated, mapped, sums, rect)
         else:
-            import torch.distributed as dist
+            from .dist import all_gather_round_robin
             mine = list(range(rank, len(rects), world))
-            per = -(-len(rects) // world)
-            send_m = torch.zeros(per, PIX2PIX_SIZE * PIX2PIX_SIZE, dtype=torch.float32, device=self.device)
-            send_s = torch.zeros(per, self.P * 4, dtype=torch.float64, device=self.device)
-            for slot, (mapped, sums) in enumerate(self.fitted_patches(work, base, [rects[i] for i in mine], rf)):
-                send_m[slot].copy_(mapped.view(-1))
-                send_s[slot].copy_(sums)
-            all_m = torch.empty(world * per, PIX2PIX_SIZE * PIX2PIX_SIZE, dtype=torch.float32, device=self.device)
-            all_s = torch.empty(world * per, self.P * 4, dtype=torch.float64, device=self.device)
-            dist.all_gather_into_tensor(all_m, send_m, group=group)
-            dist.all_gather_into_tensor(all_s, send_s, group=group)
+            got = list(self.fitted_patches(work, base, [rects[i] for i in mine], rf))
+            loc_m = torch.stack([m.view(-1) for m, _ in got]) if got else torch.zeros(0, PIX2PIX_SIZE * PIX2PIX_SIZE, dtype=torch.float32, device=self.device)
+            loc_s = torch.stack([q for _, q in got]) if got else torch.zeros(0, self.P * 4, dtype=torch.float64, device=self.device)
+            all_m = all_gather_round_robin(loc_m, len(rects), group)          # the path's one exchange: the fitted patches ...
+            all_s = all_gather_round_robin(loc_s, len(rects), group)          # ... and their five fp64 sums
             for i, rect in enumerate(rects):                                # the blend is order dependent: every rank replays it in order
-                r, slot = i % world, i // world
-                self.blend(updated, all_m[r * per + slot].view(PIX2PIX_SIZE, PIX2PIX_SIZE), all_s[r * per + slot], rect)
+                self.blend(updated, all_m[i].view(PIX2PIX_SIZE, PIX2PIX_SIZE), all_s[i], rect)
         out = self._cubic(updated.data_ptr(), ww, wh, ww, H, W)
         return out.cpu().numpy() if to_host else out

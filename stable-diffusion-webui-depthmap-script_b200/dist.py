@@ -36,3 +36,29 @@ def all_gather_batch(local, n_items: int, group=None):
     parts = [out[r * max_n: r * max_n + (sizes[r][1] - sizes[r][0])] for r in range(world)]
     full = torch.cat(parts, dim=0).contiguous()
     return full.view(local.dtype).reshape((n_items,) + tuple(local.shape[1:]))
+
+
+def round_robin_owner(i: int, world: int):
+    """BOOST deals patch i to rank i % world, which keeps it in slot i // world (patches are sorted largest first, so a round-robin
+    deal balances the work better than contiguous slices)."""
+    return i % world, i // world
+
+
+def all_gather_round_robin(local, n_items: int, group=None):
+    """local: [k, ...] = this rank's items i = rank, rank + world, ... (in that order) of an n_items list dealt round-robin ->
+    [n_items, ...] in item order on every rank, with ONE all-gather (ranks with fewer items are zero-padded to ceil(n / world) slots)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = -(-n_items // world)
+    mine = len(range(rank, n_items, world))
+    assert local.shape[0] == mine, "local items do not match the round-robin deal"
+    send = local.new_zeros((per,) + tuple(local.shape[1:]))
+    if mine:
+        send[:mine].copy_(local)
+    out = local.new_empty((world * per,) + tuple(local.shape[1:]))
+    if per:
+        dist.all_gather_into_tensor(out, send.contiguous(), group=group)
+    idx = [r * per + slot for r, slot in (round_robin_owner(i, world) for i in range(n_items))]
+    return out[torch.tensor(idx, dtype=torch.long, device=out.device)] if n_items else out[:0]

@@ -94,3 +94,43 @@ def test_video_halo_exchange_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _round_robin_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from depthmap_b200.dist import all_gather_round_robin, round_robin_owner
+    ok = True
+    for n in (5, 4, 1, 0):                          # BOOST's patch exchange: uneven deals, a rank without patches, no patch at all
+        full32 = torch.arange(n * 7, dtype=torch.float32).reshape(n, 7) * 0.5 + 1.0
+        full64 = (torch.arange(n * 3, dtype=torch.float64).reshape(n, 3) + 0.25) ** 2
+        mine = list(range(rank, n, world))
+        ok = ok and all(round_robin_owner(i, world) == (rank, k) for k, i in enumerate(mine))
+        g32 = all_gather_round_robin(full32[mine].clone() if mine else full32[:0].clone(), n)
+        g64 = all_gather_round_robin(full64[mine].clone() if mine else full64[:0].clone(), n)
+        ok = ok and g32.dtype == torch.float32 and g64.dtype == torch.float64 and torch.equal(g32, full32) and torch.equal(g64, full64)
+        # the order-dependent blend every rank replays after the exchange: the same sequence of updates on every rank
+        acc = torch.zeros(7, dtype=torch.float32)
+        for i in range(n):
+            acc = acc * 0.75 + g32[i] * float(g64[i, 0])
+        ref = torch.zeros(7, dtype=torch.float32)
+        for i in range(n):
+            ref = ref * 0.75 + full32[i] * float(full64[i, 0])
+        ok = ok and torch.equal(acc, ref)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_boost_patch_exchange_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_round_robin_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
