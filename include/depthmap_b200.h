@@ -154,10 +154,9 @@ int dm_conv3x3_f16(const void *act, int B, int H, int W, int Cin, const void *Wt
 int dm_attention_f16(const void *qkv, int B, int N, int H, float scale, const void *bias, int bias_ld, void *out, void *stream);
 /* Same, with the BEiT relative-position bias generated on the fly (dmidas/backbones/beit.py:29-62): rel_table_log2e is
  * fp32 [H, nrd] = the per-head bias table already resized to the gh x gw window, multiplied by log2(e);
- * nrd = (2gh-1)(2gw-1)+3, N = gh*gw+1 tokens (class token first); rel_rowmax_log2e is fp32 [H, N] = max over keys of the
- * bias of each query (same scaling), a setup-time constant that gives the online softmax its row-max upper bound.
- * No [H,N,N] bias tensor is read by the kernel.  rel_rowmax_log2e may be NULL (only the round-1 kernel, selected with
- * DEPTHMAP_B200_ATTN_FWD3=1, uses it). */
+ * nrd = (2gh-1)(2gw-1)+3, N = gh*gw+1 tokens (class token first).  No [H,N,N] bias tensor is read by the kernel.
+ * rel_rowmax_log2e (fp32 [H, N], the per-query maximum of the bias) was an input of the round-1 kernel; the current kernel computes
+ * exact row maxima itself and ignores it: pass NULL (the parameter stays for ABI stability). */
 int dm_attention_relpos_f16(const void *qkv, int B, int gh, int gw, int H, float scale, const float *rel_table_log2e,
                             const float *rel_rowmax_log2e, int nrd, void *out, void *stream);
 /* uint8 RGB [B,H,W,3] -> (cv2-style bicubic resize to net_h x net_w) -> (x/255 - mean)/std -> fp16 patch matrix

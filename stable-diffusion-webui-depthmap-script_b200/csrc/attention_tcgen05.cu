@@ -49,21 +49,13 @@ constexpr int AT_Q_BYTES = AT_BQ * AT_D * 2;        // 16 KB
 constexpr int AT_KV_BYTES = AT_BKV * AT_D * 2;      // 16 KB each for K and V
 constexpr int AT_P_BYTES = AT_BQ * AT_BKV * 2;      // 32 KB (two 64-key swizzle atoms)
 constexpr int AT_STAGES = 2;
-constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * 2 * AT_KV_BYTES + AT_P_BYTES + 256;  // base is __align__(1024); 2 CTAs fit one SM
-constexpr int AT_TMEM_COLS = 256;                   // S: cols [0,128), PV staging: cols [128,192)
-
 // =====================================================================================================================
-// Ping-pong variant (the default): one CTA owns TWO 128-query tiles of one (head, image) and runs two softmax
-// warpgroups.  While warpgroup A exponentiates S_A(j) the tensor core computes S_B(j) = Q_B K_j^T and P_A V_j, so the
-// MUFU-bound softmax of one tile hides behind the MMAs of the other, and every SM sub-partition hosts two softmax
-// warps whose TMEM / shared-memory latencies overlap.  K_j / V_j are fetched once for both query tiles.
-//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: softmax group A | warps 6-9: softmax group B
-// TMEM (512 columns): S_A [0,128) S_B [128,256) PV_A [256,336) PV_B [352,432).
-//
-// What keeps the softmax loop short (it is the critical resource: ~4 issue slots + 1 MUFU per score):
-//   * the PV MMA runs with N = 80: 64 value dims + a 16-wide block of ONES (2 KB of fp16 1.0 in smem, reached through
-//     the MN-major descriptor's leading-dimension offset), so column 64 of PV is the row sum of P exactly as the tensor
-//     core saw it — no unpack-and-add of the rounded probabilities in the loop;
+// Tiling shared by the kernel below: one CTA owns TWO 128-query tiles (A, B) of one (head, image).  While the softmax warps of
+// tile A exponentiate S_A(j) the tensor core computes S_B(j) = Q_B K_j^T and P_A V_j, so the MUFU-bound softmax of one tile hides
+// behind the MMAs of the other; K_j / V_j are fetched once for both tiles.  Every query row is owned by a PAIR of threads (warps w
+// and w + 4 of a group share a TMEM lane quadrant): each exponentiates 64 of the 128 key columns of a tile and keeps 32 of the 64
+// output dims; the pair agrees on the running maximum through a 2-slot shared-memory mailbox and a 64-thread named barrier.
+// What keeps the softmax loop short (it is the critical resource):
 //   * score = s * scale + (bias - m) is one FADD2 + one FFMA2 per PAIR of columns (fp32x2), the tile max is FMNMX3;
 //   * key tiles are as wide as they need to be: S and PV of the last tile use N / K = ceil16(valid keys), not 128;
 //   * lazy running max (rescale only when the tile max exceeds the running max by 2^8).
@@ -72,8 +64,10 @@ constexpr int AT_TMEM_COLS = 256;                   // S: cols [0,128), PV stagi
 // table[base_q - koff_k] — no [H,N,N] tensor is ever read (the reference materialises it per block per forward)
 // | 3 the same table for grids with gw % 16 == 0 (BEiT-512: 32x32): the tiling is shifted by the class token, i.e. query
 // and key tiles start at token 1, so every 16-key chunk lies inside one grid row and its 16 biases are the CONTIGUOUS
-// table entries base_q - koff(chunk) - i: one LDS with an immediate offset per score, no per-key index arithmetic and no
-// masks.  The class-token KEY is a 16-wide tail tile; the class-token QUERY row is done by attention_cls_row_kernel.
+// table entries base_q - koff(chunk) - i: no per-key index arithmetic and no masks.  The class-token KEY is a 16-wide tail
+// tile; the class-token QUERY row is done by attention_cls_row_kernel.
+// (The round-1 kernels — one thread per row, then P through shared memory with a fold per tile — are in the history; the
+// measurements that led from them to this one are in DESIGN.md (d).)
 // =====================================================================================================================
 struct Attn2Params {
     AttnParams a;
@@ -83,14 +77,8 @@ struct Attn2Params {
     int phase_token;          // fwd4: alternate the two query tiles' exponentiation phases (see attention_fwd4_kernel)
 };
 
-constexpr int A2_THREADS = 64 + 256;
-constexpr int A2_Q_BYTES = 2 * AT_Q_BYTES;                 // 32 KB
-constexpr int A2_KV_BYTES = AT_STAGES * 2 * AT_KV_BYTES;   // 64 KB
-constexpr int A2_P_BYTES = 2 * AT_P_BYTES;                 // 64 KB
 constexpr int A2_ONES_BYTES = 2048;                        // 16 key rows x 128 B of fp16 1.0
-constexpr int A2_TAB_BYTES = 16384 + 4096;                 // fp32 table (<= 4096 entries) + key offsets
-constexpr int A2_SMEM_BASE = A2_Q_BYTES + A2_KV_BYTES + A2_P_BYTES + A2_ONES_BYTES + 256;
-constexpr int A2_PV_N = 80, A2_PV_STRIDE = 96;
+constexpr int A2_PV_N = 80;                                // P through shared memory (PTMEM = false): 64 value dims + a 16-wide block of ones -> row sums
 
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
     uint64_t r;
@@ -122,346 +110,8 @@ __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
 struct TagTrue { static constexpr bool value = true; };
 struct TagFalse { static constexpr bool value = false; };
 
-// =====================================================================================================================
-// Two-threads-per-row variant (the default): same tiling, barriers and MMA schedule as attention_fwd2_kernel, but every
-// query row is owned by a PAIR of threads (warps w and w+4 of a group share a TMEM lane quadrant): each exponentiates 64
-// of the 128 key columns of a tile and keeps 32 of the 64 output dims.  The softmax loop is a chain of fixed-latency
-// dependencies (TMEM load -> FFMA2 -> MUFU -> pack -> STS) and with one warp per scheduler and group (fwd2) the schedulers
-// sit in `wait` stalls ~3/4 of the time; 16 softmax warps give every scheduler four independent instruction streams.
-//   warps 0-3: TMA producer, MMA issuer, two idle (they complete the warpgroup so it can shrink to 24 registers)
-//   warps 4-19: softmax; idx = warp - 4: group = idx / 8 (query tile A / B), half = (idx / 4) % 2, quadrant = idx % 4
-// The two threads of a row agree on the running max through a 2-slot shared-memory mailbox and a 64-thread named barrier
-// per (group, quadrant) once per key tile.
-// =====================================================================================================================
-constexpr int A3_THREADS = 128 + 512;
-constexpr int A3_XCH_BYTES = 2 * 2 * 128 * 2 * 4;   // [slot][group][row][half] floats
-constexpr int A3_SMEM_BASE = A2_SMEM_BASE + A3_XCH_BYTES;
-
-template <int BIAS_MODE>
-__global__ void __launch_bounds__(A3_THREADS, 1) attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, Attn2Params pp) {
-    const AttnParams &p = pp.a;
-    constexpr bool ALIGNED = BIAS_MODE == 3;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *sQ = smem_raw;
-    uint8_t *sKV = sQ + A2_Q_BYTES;
-    uint8_t *sP = sKV + A2_KV_BYTES;
-    uint8_t *sOnes = sP + A2_P_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sOnes + A2_ONES_BYTES);
-    uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3;
-    uint64_t *s_full = bars + 5, *p_full = bars + 7, *pv_full = bars + 9;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 11);
-    float *s_xch = reinterpret_cast<float *>(smem_raw + A2_SMEM_BASE);
-    float *s_tab = reinterpret_cast<float *>(smem_raw + A3_SMEM_BASE);
-    uint16_t *s_koff = reinterpret_cast<uint16_t *>(smem_raw + A3_SMEM_BASE + 16384);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int tok0 = ALIGNED ? 1 : 0;
-    const int ntok = p.N - tok0;
-    const int num_main = (ntok + AT_BKV - 1) / AT_BKV;
-    const int num_kv = num_main + (ALIGNED ? 1 : 0);
-    const int q0 = qp * 2 * AT_BQ;
-    const bool b_active = q0 + AT_BQ < ntok;
-    const int row_base = b * p.N;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmQKV);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 256); mbar_init(&pv_full[g], 1); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_ptr, 512);
-    for (int i = threadIdx.x; i < A2_ONES_BYTES / 4; i += A3_THREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3c003c00u;
-    if (BIAS_MODE >= 2) {
-        const float *tab = pp.rel_table + (size_t)h * pp.nrd;
-        for (int i = threadIdx.x; i < pp.nrd; i += A3_THREADS) s_tab[i] = __ldg(tab + i);
-        if (ALIGNED) {
-            for (int c = threadIdx.x; c < num_main * (AT_BKV / 16); c += A3_THREADS) {
-                const int t = c * 16;
-                s_koff[c] = (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw));
-            }
-        } else {
-            for (int k = threadIdx.x; k < num_kv * AT_BKV; k += A3_THREADS) {
-                const int t = k - 1;
-                s_koff[k] = (k >= 1 && k < p.N) ? (uint16_t)((t / pp.gw) * (2 * pp.gw - 1) + (t % pp.gw)) : (uint16_t)0;
-            }
-        }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (warp == 0 && lane == 0) {
-            mbar_arrive_expect_tx(q_full, b_active ? 2 * AT_Q_BYTES : AT_Q_BYTES);
-            tma_load_2d(sQ, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0);
-            if (b_active) tma_load_2d(sQ + AT_Q_BYTES, &tmQKV, q_full, h * AT_D, row_base + tok0 + q0 + AT_BQ);
-            for (int j = 0; j < num_kv; ++j) {
-                const int s = j & 1;
-                const int key0 = (ALIGNED && j == num_main) ? 0 : tok0 + j * AT_BKV;
-                mbar_wait_backoff(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-                uint8_t *sk = sKV + s * 2 * AT_KV_BYTES, *sv = sk + AT_KV_BYTES;
-                mbar_arrive_expect_tx(&kv_full[s], 2 * AT_KV_BYTES);
-                tma_load_2d(sk, &tmQKV, &kv_full[s], p.C + h * AT_D, row_base + key0);
-                tma_load_2d(sv, &tmQKV, &kv_full[s], 2 * p.C + h * AT_D, row_base + key0);
-            }
-        } else if (warp == 1 && lane == 0) {
-            constexpr uint32_t idesc_pv = make_idesc_f16(AT_BQ, A2_PV_N, 0, 0, 1);
-            const uint32_t ones_addr = smem_u32(sOnes);
-            mbar_wait_backoff(q_full, 0);
-            const int ngroups = b_active ? 2 : 1;
-            auto tile_cols = [&](int j) {
-                const int nvalid = (ALIGNED && j == num_main) ? 1 : min(AT_BKV, ntok - j * AT_BKV);
-                return (nvalid + 15) & ~15;
-            };
-            auto issue_s = [&](int g, int j) {
-                const uint32_t idesc_qk = make_idesc_f16(AT_BQ, tile_cols(j), 0, 0, 0);
-                const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sKV + (j & 1) * 2 * AT_KV_BYTES));
-                const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ + g * AT_Q_BYTES));
-#pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k)
-                    umma_f16(tmem_base + g * 128, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_qk, k != 0);
-                umma_commit(&s_full[g]);
-            };
-            mbar_wait_backoff(&kv_full[0], 0);
-            tc_fence_after();
-            for (int g = 0; g < ngroups; ++g) issue_s(g, 0);
-            for (int j = 0; j < num_kv; ++j) {
-                const int s = j & 1;
-                const int ncols = tile_cols(j);
-                const bool has_next = j + 1 < num_kv;
-                const uint32_t sv = smem_u32(sKV + s * 2 * AT_KV_BYTES) + AT_KV_BYTES;
-                for (int g = 0; g < ngroups; ++g) {
-                    mbar_wait_backoff(&p_full[g], j & 1);
-                    tc_fence_after();
-                    const uint32_t sp = smem_u32(sP + g * AT_P_BYTES);
-                    for (int k = 0; k < (ncols >> 4); ++k) {
-                        const uint64_t pdesc = make_desc_kmajor_sw128(sp + (k >> 2) * (AT_BQ * 128) + (k & 3) * 32);
-                        const uint32_t vaddr = sv + k * 16 * 128;
-                        const uint64_t vdesc = make_desc_mnmajor_sw128(vaddr, ones_addr - vaddr);
-                        umma_f16(tmem_base + 256 + g * A2_PV_STRIDE, pdesc, vdesc, idesc_pv, k != 0);
-                    }
-                    umma_commit(&pv_full[g]);
-                    if (has_next) {
-                        if (g == 0) { mbar_wait_backoff(&kv_full[s ^ 1], ((j + 1) >> 1) & 1); tc_fence_after(); }
-                        issue_s(g, j + 1);
-                    }
-                }
-                umma_commit(&kv_empty[s]);
-            }
-        }
-    } else {
-        // the register pool of the CTA is what it was launched with (640 x 96); the producer warpgroup hands back
-        // 128 x (96 - 24), which lets the four softmax warpgroups grow to 112 (4 x 128 x 16 = 8192 <= 9216) - asking for more
-        // than the pool holds blocks forever
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-        const int idx = warp - 4;
-        const int g = idx >> 3, hh = (idx >> 2) & 1, q = idx & 3;
-        if (!(g == 1 && !b_active)) {
-        const int row = q * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const uint32_t tmem_S = tmem_base + g * 128 + lane_off, tmem_PV = tmem_base + 256 + g * A2_PV_STRIDE + lane_off;
-        uint8_t *sPg = sP + g * AT_P_BYTES;
-        const int pair_bar = 1 + g * 4 + q;            // named barrier of the two warps that share these 32 rows
-        const int tq = q0 + g * AT_BQ + row;
-        const bool q_ok = tq < ntok;
-        const int qi = tok0 + tq;
-        float m_run = -INFINITY;
-        float o[AT_D / 2 + 1];                         // this half's 32 output dims + the running row sum
-#pragma unroll
-        for (int d = 0; d <= AT_D / 2; ++d) o[d] = 0.f;
-        constexpr float LOG2E = 1.4426950408889634f;
-        const __half *brow = BIAS_MODE == 1 ? p.bias + ((size_t)h * p.N + (q_ok ? qi : 0)) * p.bias_ld : nullptr;
-        int rp_base = 0, rp_mult = 1;
-        float rp_k0 = 0.f, rp_rowmax = 0.f;
-        if (BIAS_MODE >= 2) {
-            const int qq = q_ok ? qi : 1;
-            rp_rowmax = __ldg(pp.rel_rowmax + (size_t)h * p.N + qq);
-            if (qq == 0) { rp_base = pp.nrd - 3; rp_mult = 0; rp_k0 = s_tab[pp.nrd - 1]; }
-            else {
-                const int t = qq - 1, qy = t / pp.gw, qx = t % pp.gw;
-                rp_base = (qy + pp.gh - 1) * (2 * pp.gw - 1) + (qx + pp.gw - 1);
-                rp_k0 = s_tab[pp.nrd - 2];
-            }
-        }
-        const uint64_t scale2 = pack2(p.scale_log2e, p.scale_log2e);
-        int xch_n = 0;
-        // row-wide max of a per-thread value: mailbox slot (xch_n & 1), one named barrier between the write and the read
-        auto pair_max = [&](float v) {
-            float *slot = s_xch + (((xch_n & 1) * 2 + g) * 128 + row) * 2;
-            slot[hh] = v;
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            const float other = slot[hh ^ 1];
-            ++xch_n;
-            return fmaxf(v, other);
-        };
-        auto fold_pv = [&]() {
-            uint32_t r0[32];
-            tmem_ld_32x32(tmem_PV + hh * 32, r0);
-            const uint32_t rs = tmem_ld_32x1(tmem_PV + 64);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(r0[i]);
-            o[AT_D / 2] += __uint_as_float(rs);
-        };
-
-        for (int j = 0; j < num_kv; ++j) {
-            const bool tail = ALIGNED && j == num_main;
-            const int kbase = tail ? 0 : tok0 + j * AT_BKV;
-            const int nvalid = tail ? 1 : min(AT_BKV, ntok - j * AT_BKV);
-            const int ncols = (nvalid + 15) & ~15;
-            const int cbeg = hh * 64, cend = min(ncols, cbeg + 64);     // this thread's columns of the tile
-            mbar_wait(&s_full[g], j & 1);
-            tc_fence_after();
-            if (j == 0) {
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c0 = cbeg; c0 < cend; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld_32x16(tmem_S + c0, r);
-                    tmem_ld_wait();
-                    if (BIAS_MODE == 1) {
-                        const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
-#pragma unroll
-                        for (int gq = 0; gq < 2; ++gq) {
-                            const uint4 u = __ldg(bp + gq);
-                            const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float2 bf = __half22float2(h2[k]);
-                                const int i = gq * 8 + 2 * k;
-                                float s0 = fmaf(bf.x, LOG2E, __uint_as_float(r[i]) * p.scale_log2e);
-                                float s1 = fmaf(bf.y, LOG2E, __uint_as_float(r[i + 1]) * p.scale_log2e);
-                                s0 = (c0 + i < nvalid) ? s0 : -INFINITY; s1 = (c0 + i + 1 < nvalid) ? s1 : -INFINITY;
-                                mx = fmaxf(mx, fmaxf(s0, s1));
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c0 + i < nvalid) ? __uint_as_float(r[i]) : -INFINITY);
-                    }
-                }
-                mx = pair_max(mx);
-                if (BIAS_MODE == 0) mx *= p.scale_log2e;
-                if (BIAS_MODE >= 2) mx = fmaf(mx, p.scale_log2e, rp_rowmax);
-                m_run = mx;
-            } else {
-                mbar_wait(&pv_full[g], (j - 1) & 1);
-                tc_fence_after();
-                fold_pv();
-            }
-            for (int attempt = 0;; ++attempt) {
-                float mx_rel = -INFINITY;
-                const float neg_m = -m_run;
-                const uint64_t negm2 = pack2(neg_m, neg_m);
-                auto chunk = [&](const uint32_t (&r)[16], int c0, auto partial_tag) {
-                    constexpr bool PARTIAL = decltype(partial_tag)::value;
-                    float bv[16];
-                    if (BIAS_MODE == 1) {
-                        const uint4 *bp = reinterpret_cast<const uint4 *>(brow + kbase + c0);
-#pragma unroll
-                        for (int gq = 0; gq < 2; ++gq) {
-                            const uint4 u = __ldg(bp + gq);
-                            const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) { const float2 bf = __half22float2(h2[k]); bv[gq * 8 + 2 * k] = bf.x * LOG2E; bv[gq * 8 + 2 * k + 1] = bf.y * LOG2E; }
-                        }
-                    } else if (BIAS_MODE == 2) {
-                        const uint4 *kp = reinterpret_cast<const uint4 *>(s_koff + kbase + c0);
-#pragma unroll
-                        for (int gq = 0; gq < 2; ++gq) {
-                            const uint4 u = kp[gq];
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                bv[gq * 8 + 2 * k] = s_tab[rp_base - rp_mult * (int)(w[k] & 0xffffu)];
-                                bv[gq * 8 + 2 * k + 1] = s_tab[rp_base - rp_mult * (int)(w[k] >> 16)];
-                            }
-                        }
-                        if (kbase + c0 == 0) bv[0] = rp_k0;
-                    } else if (BIAS_MODE == 3) {
-                        if (tail) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) bv[i] = rp_k0;
-                        } else {
-                            const float *tp = s_tab + (rp_base - (int)s_koff[(j * AT_BKV + c0) >> 4]);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) bv[i] = *(tp - i);
-                        }
-                    }
-                    uint32_t packed[8];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const uint64_t b2 = BIAS_MODE == 0 ? negm2 : add2(pack2(bv[i], bv[i + 1]), negm2);
-                        float t0, t1;
-                        unpack2(fma2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, b2), t0, t1);
-                        if (PARTIAL) { t0 = (c0 + i < nvalid) ? t0 : -INFINITY; t1 = (c0 + i + 1 < nvalid) ? t1 : -INFINITY; }
-                        mx_rel = max3(mx_rel, t0, t1);
-                        const __half2 h2 = __floats2half2_rn(ex2_approx(t0), ex2_approx(t1));
-                        packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
-                    }
-                    uint8_t *atom = sPg + (c0 >> 6) * (AT_BQ * 128) + row * 128;
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const int ch = (((c0 & 63) >> 3) + t) ^ (row & 7);
-                        *reinterpret_cast<uint4 *>(atom + ch * 16) = make_uint4(packed[4 * t], packed[4 * t + 1], packed[4 * t + 2], packed[4 * t + 3]);
-                    }
-                };
-                if (cbeg < cend) {
-                    uint32_t ra[16], rb[16];
-                    tmem_ld_32x16(tmem_S + cbeg, ra);
-#pragma unroll 1
-                    for (int c0 = cbeg; c0 < cend; c0 += 32) {
-                        tmem_ld_wait();
-                        const bool has_b = c0 + 16 < cend;
-                        if (has_b) tmem_ld_32x16(tmem_S + c0 + 16, rb);
-                        if (c0 + 16 > nvalid) chunk(ra, c0, TagTrue()); else chunk(ra, c0, TagFalse());
-                        if (has_b) {
-                            tmem_ld_wait();
-                            if (c0 + 32 < cend) tmem_ld_32x16(tmem_S + c0 + 32, ra);
-                            if (c0 + 32 > nvalid) chunk(rb, c0 + 16, TagTrue()); else chunk(rb, c0 + 16, TagFalse());
-                        }
-                    }
-                }
-                mx_rel = pair_max(mx_rel);                  // both threads of the row see the same value ...
-                const bool need = mx_rel > 8.0f;
-                if (!__any_sync(0xffffffffu, need)) break;  // ... so both warps of the pair take the same (warp-uniform) decision
-                if (need) {
-                    const float alpha = ex2_approx(-mx_rel);
-#pragma unroll
-                    for (int d = 0; d <= AT_D / 2; ++d) o[d] *= alpha;
-                    m_run += mx_rel;
-                }
-            }
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(&p_full[g]);
-        }
-        mbar_wait(&pv_full[g], (num_kv - 1) & 1);
-        tc_fence_after();
-        fold_pv();
-        if (q_ok) {
-            const float inv = 1.0f / o[AT_D / 2];
-            __half *dst = p.out + (size_t)(row_base + qi) * p.C + h * AT_D + hh * 32;
-#pragma unroll
-            for (int d = 0; d < AT_D / 2; d += 8) {
-                uint4 u;
-                __half2 *h2 = reinterpret_cast<__half2 *>(&u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(o[d + 2 * k] * inv, o[d + 2 * k + 1] * inv);
-                *reinterpret_cast<uint4 *>(dst + d) = u;
-            }
-        }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
+// pair mailbox of the two threads that share a query row: [slot][group][row][half] floats
+constexpr int A3_XCH_BYTES = 2 * 2 * 128 * 2 * 4;
 
 // Class-token query row of the aligned BEiT mode: one CTA per (head, image), plain SIMT (N scores of one row).
 // Its bias is the constant class->patch entry (nrd-3) for every key and the class->class entry (nrd-1) for key 0
@@ -542,9 +192,8 @@ __global__ void __launch_bounds__(256) attention_cls_row_kernel(const __half *__
 }
 
 // =====================================================================================================================
-// attention_fwd4_kernel (the default).  Same tiling as fwd3 (one CTA = two 128-query tiles of one (head, image), two
-// threads per query row, P through the swizzled K-major smem tile, PV with N = 80 whose ones block yields the row sums),
-// restructured around what the round-1 profile showed (softmax warps idle 25% of the time waiting for the next S,
+// attention_fwd4_kernel.  One CTA = two 128-query tiles of one (head, image), two threads per query row; built around what the
+// round-1 profile showed (softmax warps idle 25% of the time waiting for the next S,
 // 15.6 issued instructions per exponential where the MUFU pipe allows 8):
 //   * S leaves TMEM at once: a thread loads its 64 scores of the tile into registers and the warp releases the S
 //     accumulator (s_free) BEFORE any arithmetic, so S(j+1) = Q K_{j+1}^T is computed while tile j is exponentiated;
@@ -557,7 +206,7 @@ __global__ void __launch_bounds__(256) attention_cls_row_kernel(const __half *__
 //   * BEiT bias (mode 3): the head's table is held REVERSED, twice (the second copy shifted by one element), so the 16
 //     consecutive biases of a 16-key chunk are eight 8-byte-aligned LDS.64 with immediate offsets;
 //   * warp-elected mbarrier arrivals (8 per tile instead of 256).
-//   warp 0: TMA producer | warp 1 / 2: MMA issuer of tile A / B | warp 3: idle | warps 4-19: softmax (as fwd3)
+//   warp 0: TMA producer | warp 1 / 2: MMA issuer of tile A / B | warp 3: idle | warps 4-19: softmax; idx = warp - 4: group = idx / 8 (tile A / B), half = (idx / 4) % 2, quadrant = idx % 4
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,336) O_B [352,432); columns 64..79 of O are the ones block.
 // =====================================================================================================================
 constexpr int A4_THREADS = 128 + 512;
@@ -571,7 +220,7 @@ constexpr int A4_XCH_OFF = A4_BAR_OFF + 256;                  // pair mailbox [s
 constexpr int A4_TAB_OFF = A4_XCH_OFF + A3_XCH_BYTES;         // relative-position table(s) + key offsets (modes 2, 3)
 constexpr int A4_SMEM_MAX = 227 * 1024;
 constexpr int A4_TAB_MAX = A4_SMEM_MAX - A4_TAB_OFF;
-constexpr int A4_O_COL = 256, A4_O_STRIDE = 96;
+constexpr int A4_O_STRIDE = 96;
 constexpr int A4_POLY_DEFAULT = 0;
 
 __device__ __forceinline__ void mbar_wait_role(uint64_t *bar, uint32_t parity) {
@@ -1043,16 +692,7 @@ static int launch_attn4(const CUtensorMap &tm, const Attn2Params &pp, cudaStream
     const int ntok = pp.a.N - (MODE == 3 ? 1 : 0);
     const int num_main = (ntok + AT_BKV - 1) / AT_BKV, num_kv = num_main + (MODE == 3 ? 1 : 0);
     dim3 grid((ntok + 2 * AT_BQ - 1) / (2 * AT_BQ), pp.a.H, pp.a.B);
-    static int use_fwd3 = -1;     // DEPTHMAP_B200_ATTN_FWD3=1: the round-1 kernel, kept for A/B timing
-    if (use_fwd3 < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_FWD3"); use_fwd3 = (e && e[0] == '1') ? 1 : 0; }
-    if (use_fwd3 && !(MODE >= 2 && (pp.nrd > 4096 || !pp.rel_rowmax))) {
-        const int smem = A3_SMEM_BASE + (MODE >= 2 ? A2_TAB_BYTES : 0);
-        static PerDeviceFlag configured;
-        if (!configured.test_and_set())
-            DM_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attention_fwd3_kernel<MODE><<<grid, A3_THREADS, smem, stream>>>(tm, pp);
-        DM_LAUNCH_CHECK("attention_fwd3_kernel");
-    } else {
+    {
         const size_t tab = attn4_table_bytes(MODE, pp.nrd, pp.a.N, num_main, num_kv);
         if (tab > (size_t)A4_TAB_MAX) { set_error("attention: relative-position table (%d entries) does not fit in shared memory", pp.nrd); return DM_E_UNSUPPORTED; }
         static int p_tmem = -1;       // DEPTHMAP_B200_ATTN_PTMEM=0: P through shared memory (the first fwd4 form), kept for A/B timing

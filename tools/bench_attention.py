@@ -1,5 +1,5 @@
 """Tool: times the fused attention kernel alone on the two bench shapes (CUDA events, 20 launches after 3 warm-ups).
-DEPTHMAP_B200_ATTN_FWD3=1 selects the round-1 kernel for an A/B comparison (read once per process).
+DEPTHMAP_B200_ATTN_PTMEM=0 / DEPTHMAP_B200_ATTN_TOKEN=0 / DEPTHMAP_B200_ATTN_POLY=n select the measured variants of the kernel for A/B timing (read once per process).
 usage: python tools/bench_attention.py [beit|dav2|both]"""
 import os
 import sys
@@ -29,7 +29,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1e3
-        print(f"{name}: {us:.1f} us/launch  {flops / us * 1e-6:.1f} TFLOP/s  (fwd3={os.environ.get('DEPTHMAP_B200_ATTN_FWD3', '0')})")
+        print(f"{name}: {us:.1f} us/launch  {flops / us * 1e-6:.1f} TFLOP/s")
 
     if which in ("beit", "both"):
         B, gh, gw = 32, 32, 32
