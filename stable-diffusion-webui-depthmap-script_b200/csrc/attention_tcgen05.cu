@@ -48,7 +48,6 @@ constexpr int AT_BQ = 128, AT_BKV = 128, AT_D = 64;
 constexpr int AT_Q_BYTES = AT_BQ * AT_D * 2;        // 16 KB
 constexpr int AT_KV_BYTES = AT_BKV * AT_D * 2;      // 16 KB each for K and V
 constexpr int AT_P_BYTES = AT_BQ * AT_BKV * 2;      // 32 KB (two 64-key swizzle atoms)
-constexpr int AT_STAGES = 2;
 // =====================================================================================================================
 // Tiling shared by the kernel below: one CTA owns TWO 128-query tiles (A, B) of one (head, image).  While the softmax warps of
 // tile A exponentiate S_A(j) the tensor core computes S_B(j) = Q_B K_j^T and P_A V_j, so the MUFU-bound softmax of one tile hides
@@ -221,7 +220,6 @@ constexpr int A4_TAB_OFF = A4_XCH_OFF + A3_XCH_BYTES;         // relative-positi
 constexpr int A4_SMEM_MAX = 227 * 1024;
 constexpr int A4_TAB_MAX = A4_SMEM_MAX - A4_TAB_OFF;
 constexpr int A4_O_STRIDE = 96;
-constexpr int A4_POLY_DEFAULT = 0;
 
 __device__ __forceinline__ void mbar_wait_role(uint64_t *bar, uint32_t parity) {
     // single-thread roles: block in hardware (suspend-time hint) instead of polling through the issue port
@@ -269,7 +267,7 @@ __host__ __device__ __forceinline__ int attn4_nrd_pad(int nrd) { return ((nrd + 
 // the shared-memory pipe, which the profile shows to be the busiest unit (bias loads + P stores + UMMA operand fetches).  TMEM is
 // then full — S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512) — so the ones block of the PV MMA
 // goes and each thread sums its 64 probabilities itself (the two halves of a row meet in the mailbox at the end).
-template <int BIAS_MODE, bool PTMEM, int POLY = 0>
+template <int BIAS_MODE, bool PTMEM>
 __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, Attn2Params pp) {
     const AttnParams &p = pp.a;
     constexpr bool ALIGNED = BIAS_MODE == 3;
@@ -598,26 +596,10 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_fwd4_kernel(const __g
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     float e0, e1;
-                    if (c >= 4 - POLY) {
-                        // 2^x on the FMA pipe for this chunk (the MUFU pipe, 16 lanes / SM, is the busiest unit of the exponentiation
-                        // phase): n = round(x) through the 1.5 * 2^23 magic number, f = x - n in [-0.5, 0.5], a cubic for 2^f
-                        // (max relative error 7.5e-5, six times below the fp16 rounding of P), exponent added as integer bits
-                        const float x0 = fmaxf(__uint_as_float(r[c * 16 + i]), -126.f), x1 = fmaxf(__uint_as_float(r[c * 16 + i + 1]), -126.f);
-                        const uint64_t x2 = pack2(x0, x1), mg = pack2(12582912.f, 12582912.f);
-                        const uint64_t t2 = add2(x2, mg);
-                        const uint64_t f2 = add2(x2, add2(mg, t2 ^ 0x8000000080000000ull));            // x - (t - magic)
-                        uint64_t p2 = fma2(f2, pack2(0.055171649903059006f, 0.055171649903059006f), pack2(0.2426111251115799f, 0.2426111251115799f));
-                        p2 = fma2(p2, f2, pack2(0.6932609677314758f, 0.6932609677314758f));
-                        p2 = fma2(p2, f2, pack2(0.9999280571937561f, 0.9999280571937561f));
-                        float t0, t1, q0, q1;
-                        unpack2(t2, t0, t1);
-                        unpack2(p2, q0, q1);
-                        e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
-                        e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
-                    } else {
-                        e0 = ex2_approx(__uint_as_float(r[c * 16 + i]));
-                        e1 = ex2_approx(__uint_as_float(r[c * 16 + i + 1]));
-                    }
+                    // (2^x on the FMA pipe for part of the tile — Cody-Waite + cubic, exponent added as integer bits — was measured and
+                    // dropped: 386 / 430 us against 364 us; the kernel is bound by issue slots, not by the MUFU pipe.  DESIGN.md (d))
+                    e0 = ex2_approx(__uint_as_float(r[c * 16 + i]));
+                    e1 = ex2_approx(__uint_as_float(r[c * 16 + i + 1]));
                     if (PTMEM) ls2 = add2(ls2, pack2(e0, e1));
                     const __half2 h2 = __floats2half2_rn(e0, e1);
                     packed[i >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
@@ -697,19 +679,7 @@ static int launch_attn4(const CUtensorMap &tm, const Attn2Params &pp, cudaStream
         if (tab > (size_t)A4_TAB_MAX) { set_error("attention: relative-position table (%d entries) does not fit in shared memory", pp.nrd); return DM_E_UNSUPPORTED; }
         static int p_tmem = -1;       // DEPTHMAP_B200_ATTN_PTMEM=0: P through shared memory (the first fwd4 form), kept for A/B timing
         if (p_tmem < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_PTMEM"); p_tmem = (e && e[0] == '0') ? 0 : 1; }
-        static int poly = -1;         // DEPTHMAP_B200_ATTN_POLY=n: n of the 4 chunks of a thread's tile take 2^x on the FMA pipe
-        if (poly < 0) { const char *e = getenv("DEPTHMAP_B200_ATTN_POLY"); poly = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : A4_POLY_DEFAULT; }
-        if (p_tmem && poly == 1) {
-            static PerDeviceFlag configured;
-            if (!configured.test_and_set())
-                DM_CUDA_CHECK(cudaFuncSetAttribute((attention_fwd4_kernel<MODE, true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_MAX));
-            attention_fwd4_kernel<MODE, true, 1><<<grid, A4_THREADS, A4_TAB_OFF + tab, stream>>>(tm, pp);
-        } else if (p_tmem && poly == 2) {
-            static PerDeviceFlag configured;
-            if (!configured.test_and_set())
-                DM_CUDA_CHECK(cudaFuncSetAttribute((attention_fwd4_kernel<MODE, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_MAX));
-            attention_fwd4_kernel<MODE, true, 2><<<grid, A4_THREADS, A4_TAB_OFF + tab, stream>>>(tm, pp);
-        } else if (p_tmem) {
+        if (p_tmem) {
             static PerDeviceFlag configured;
             if (!configured.test_and_set())
                 DM_CUDA_CHECK(cudaFuncSetAttribute((attention_fwd4_kernel<MODE, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_MAX));
