@@ -1,5 +1,5 @@
 """Tool: times the fused attention kernel alone on the two bench shapes (CUDA events, 20 launches after 3 warm-ups).
-DEPTHMAP_B200_ATTN_PTMEM=0 / DEPTHMAP_B200_ATTN_TOKEN=0 / DEPTHMAP_B200_ATTN_POLY=n select the measured variants of the kernel for A/B timing (read once per process).
+DEPTHMAP_B200_ATTN_PTMEM=0 / DEPTHMAP_B200_ATTN_TOKEN=0 select the measured variants of the kernel for A/B timing (read once per process).
 usage: python tools/bench_attention.py [beit|dav2|both]"""
 import os
 import sys
